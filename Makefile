@@ -1,0 +1,52 @@
+# hast-b200 build.  Everything is built in-tree so that the artefacts travel
+# with the gpurun snapshot:
+#   hast_b200/lib/libhast_b200.so   the C-ABI engine (CUDA, sm_100a only)
+#   hast_b200/lib/libhast_tools.so  synthetic-data helper (FASTQ text emitter)
+#   bin/classify, bin/mergeResult   drop-in replacements for the reference stage-01 binaries
+#   oracle/liboracle.so, oracle/_ref/*   test infrastructure (see oracle/Makefile)
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX  ?= g++
+CC   ?= gcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function
+CUDA_HOME ?= /usr/local/cuda
+
+LIB := hast_b200/lib/libhast_b200.so
+TOOLS := hast_b200/lib/libhast_tools.so
+CSRC := hast_b200/csrc
+HOST := hast_b200/host
+
+.PHONY: all lib tools host oracle clean sass
+all: lib tools host oracle
+
+lib: $(LIB)
+$(LIB): $(CSRC)/hast_b200.cu $(CSRC)/kernels.cuh $(CSRC)/table.cuh $(CSRC)/kmer.cuh include/hast_b200.h
+	@mkdir -p hast_b200/lib
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared $< -o $@ -ldl 2> hast_b200/lib/ptxas.log || (cat hast_b200/lib/ptxas.log; exit 1)
+	@grep -E "registers|spill" hast_b200/lib/ptxas.log | sort | uniq -c | sort -rn | head -20 || true
+
+tools: $(TOOLS)
+$(TOOLS): hast_b200/tools/fastq_fmt.c
+	@mkdir -p hast_b200/lib
+	$(CC) -O2 -std=c11 -fPIC -shared $< -lz -o $@
+
+host: bin/classify bin/mergeResult
+HOST_SRCS := $(wildcard $(HOST)/*.cpp)
+HOST_HDRS := $(wildcard $(HOST)/*.h)
+bin/classify: $(filter-out $(HOST)/merge_result_main.cpp,$(HOST_SRCS)) $(HOST_HDRS) $(LIB) include/hast_b200.h
+	@mkdir -p bin
+	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(filter-out $(HOST)/merge_result_main.cpp,$(HOST_SRCS)) \
+	    -Lhast_b200/lib -lhast_b200 -lz -Wl,-rpath,'$$ORIGIN/../hast_b200/lib' -o $@
+bin/mergeResult: $(HOST)/merge_result_main.cpp
+	@mkdir -p bin
+	$(CXX) -O2 -g -std=c++17 -Wall $< -o $@
+
+oracle:
+	$(MAKE) -C oracle all
+
+sass: $(LIB)
+	$(CUDA_HOME)/bin/cuobjdump -sass $(LIB) > hast_b200/lib/libhast_b200.sass
+
+clean:
+	rm -rf hast_b200/lib bin
+	$(MAKE) -C oracle clean

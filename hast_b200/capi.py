@@ -1,0 +1,284 @@
+"""ctypes binding of the C ABI in ``include/hast_b200.h`` (libhast_b200.so).
+
+This is the thin Python face of the engine used by the parity tests and by
+``bench.py``; the production host program is the C++ ``bin/classify``.  There is
+no fallback: if the shared library is missing or no CUDA device is present the
+calls raise.  Reference seams are cited in the header next to each entry point
+(classify.cpp / kmer.h of 01.classify_stlfr_reads).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB_PATH = ROOT / "hast_b200" / "lib" / "libhast_b200.so"
+HEADER_PATH = ROOT / "include" / "hast_b200.h"
+
+HAST_OK = 0
+E_ARG, E_CUDA, E_STATE, E_KMER_LINE, E_SHORT_READ, E_TABLE_FULL, E_NCCL, E_K = range(-1, -9, -1)
+
+
+class HastError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"hast_b200 error {code}: {msg}")
+        self.code = code
+
+
+class TableInfo(C.Structure):
+    _fields_ = [("k", C.c_int32), ("log2_buckets", C.c_int32), ("n_buckets", C.c_uint64),
+                ("bytes", C.c_uint64), ("n_entries", C.c_uint64), ("n_displaced", C.c_uint64),
+                ("n_overflow_buckets", C.c_uint64), ("size", C.c_uint64 * 2)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in
+                ("batches", "reads", "bases", "lookups", "reads_with_n", "reads_short",
+                 "extra_probes", "kernel_launches", "h2d_bytes", "d2h_bytes")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+_vp, _u64, _u32, _i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+
+# name -> (restype, argtypes): every symbol include/hast_b200.h declares
+SIGNATURES = {
+    "hast_abi_version": (_i32, []),
+    "hast_device_count": (_i32, []),
+    "hast_create": (_i32, [_i32, C.POINTER(_vp)]),
+    "hast_destroy": (None, [_vp]),
+    "hast_last_error": (C.c_char_p, [_vp]),
+    "hast_device": (_i32, [_vp]),
+    "hast_host_alloc": (_i32, [C.POINTER(_vp), C.c_size_t]),
+    "hast_host_free": (_i32, [_vp]),
+    "hast_table_begin": (_i32, [_vp, _i32, _u64]),
+    "hast_table_add_text": (_i32, [_vp, _vp, _u64, _i32]),
+    "hast_table_add_packed": (_i32, [_vp, _vp, _u64, _i32]),
+    "hast_table_erase_seq": (_i32, [_vp, C.c_char_p, _u32, _vp, _vp, _u32, C.POINTER(_u32)]),
+    "hast_table_info_get": (_i32, [_vp, C.POINTER(TableInfo)]),
+    "hast_table_clone": (_i32, [_vp, _vp]),
+    "hast_reserve_barcodes": (_i32, [_vp, _u64]),
+    "hast_reset_counts": (_i32, [_vp]),
+    "hast_submit_batch": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32, C.POINTER(_u64)]),
+    "hast_wait_copied": (_i32, [_vp, _u64]),
+    "hast_submit_batch_device": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32]),
+    "hast_sync": (_i32, [_vp]),
+    "hast_finish": (_i32, [_vp, _vp, _u64]),
+    "hast_stats_get": (_i32, [_vp, C.POINTER(Stats)]),
+    "hast_counts_device_ptr": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
+    "hast_timer_start": (_i32, [_vp]),
+    "hast_timer_stop": (_i32, [_vp, C.POINTER(C.c_float)]),
+    "hast_comm_init_all": (_i32, [C.POINTER(_vp), _i32]),
+    "hast_comm_unique_id": (_i32, [_vp]),
+    "hast_comm_init_rank": (_i32, [_vp, _i32, _i32, _vp]),
+    "hast_extract_kmers": (_i32, [_vp, _vp, _u64, _vp, _u32, _vp, _u64, _vp]),
+    "hast_lookup": (_i32, [_vp, _vp, _u64, _vp]),
+    "hast_extract_kmers_device": (_i32, [_vp, _vp, _u64, _vp, _u32, _vp, _vp]),
+    "hast_lookup_device": (_i32, [_vp, _vp, _u64, _vp]),
+    "hast_gather_roofline": (_i32, [_vp, _u64, _u64, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def load_library(path: os.PathLike | None = None) -> C.CDLL:
+    """Load libhast_b200.so and attach the prototypes.  Raises if it is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise FileNotFoundError(
+            f"{p} not found: build it with `make lib` (or __graft_entry__.build()); "
+            "there is no Python/CPU fallback for the classification path")
+    lib = C.CDLL(str(p))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dtype) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class Engine:
+    """One context = one GPU (the reference's MultiThread worker, classify.cpp:129-236)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self._ctx = C.c_void_p()
+        rc = self.lib.hast_create(device, C.byref(self._ctx))
+        if rc:
+            raise HastError(rc, (self.lib.hast_last_error(None) or b"").decode())
+
+    # -- plumbing ---------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc:
+            raise HastError(rc, (self.lib.hast_last_error(self._ctx) or b"").decode())
+
+    def close(self):
+        if self._ctx:
+            self.lib.hast_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._ctx
+
+    # -- K1 ---------------------------------------------------------------
+    def table_begin(self, k: int, expected_keys: int):
+        self._ck(self.lib.hast_table_begin(self._ctx, k, int(expected_keys)))
+
+    def table_add_text(self, text: bytes | np.ndarray, k: int, parent: int) -> int:
+        """text = jellyfish-dump style list.  Only whole '\\n'-terminated lines are used
+        (classify.cpp:41 drops an unterminated last line)."""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else _arr(text, np.uint8)
+        n_lines = buf.size // (k + 1)
+        self._ck(self.lib.hast_table_add_text(self._ctx, _ptr(buf), n_lines, parent))
+        return n_lines
+
+    def table_add_packed(self, kmers: np.ndarray, parent: int):
+        kmers = _arr(kmers, np.uint64)
+        self._ck(self.lib.hast_table_add_packed(self._ctx, _ptr(kmers), kmers.size, parent))
+
+    def table_erase_seq(self, seq: bytes):
+        """Returns [(packed canonical k-mer, former tag)] in adaptor order."""
+        cap = max(1, len(seq))
+        er = np.zeros(cap, np.uint64)
+        tg = np.zeros(cap, np.uint8)
+        n = C.c_uint32()
+        self._ck(self.lib.hast_table_erase_seq(self._ctx, seq, len(seq), _ptr(er), _ptr(tg), cap, C.byref(n)))
+        return [(int(er[i]), int(tg[i])) for i in range(n.value)]
+
+    def table_info(self) -> TableInfo:
+        ti = TableInfo()
+        self._ck(self.lib.hast_table_info_get(self._ctx, C.byref(ti)))
+        return ti
+
+    def table_clone_from(self, other: "Engine"):
+        self._ck(self.lib.hast_table_clone(self._ctx, other._ctx))
+
+    # -- K4 state ---------------------------------------------------------
+    def reserve_barcodes(self, n: int):
+        self._ck(self.lib.hast_reserve_barcodes(self._ctx, int(n)))
+
+    def reset_counts(self):
+        self._ck(self.lib.hast_reset_counts(self._ctx))
+
+    # -- batches ----------------------------------------------------------
+    def submit_batch(self, bases: np.ndarray, read_off: np.ndarray, barcode_id: np.ndarray) -> int:
+        bases = _arr(bases, np.uint8).reshape(-1)
+        read_off = _arr(read_off, np.uint32)
+        barcode_id = _arr(barcode_id, np.uint32)
+        n_reads = barcode_id.size
+        assert read_off.size == n_reads + 1
+        t = C.c_uint64()
+        self._ck(self.lib.hast_submit_batch(self._ctx, _ptr(bases), bases.size, _ptr(read_off),
+                                            _ptr(barcode_id), n_reads, C.byref(t)))
+        # numpy buffers are pageable: keep them alive until the copy is done
+        self._ck(self.lib.hast_wait_copied(self._ctx, t.value))
+        return t.value
+
+    def submit_batch_ptr(self, bases_ptr: int, n_bases: int, off_ptr: int, bc_ptr: int, n_reads: int) -> int:
+        """Host pointers (e.g. pinned torch tensors); asynchronous, returns the ticket."""
+        t = C.c_uint64()
+        self._ck(self.lib.hast_submit_batch(self._ctx, bases_ptr, n_bases, off_ptr, bc_ptr, n_reads, C.byref(t)))
+        return t.value
+
+    def wait_copied(self, ticket: int):
+        self._ck(self.lib.hast_wait_copied(self._ctx, ticket))
+
+    def submit_batch_device(self, bases_ptr: int, n_bases: int, off_ptr: int, bc_ptr: int, n_reads: int):
+        self._ck(self.lib.hast_submit_batch_device(self._ctx, bases_ptr, n_bases, off_ptr, bc_ptr, n_reads))
+
+    def sync(self):
+        self._ck(self.lib.hast_sync(self._ctx))
+
+    def finish(self, n_barcodes: int, want_counts: bool = True) -> np.ndarray | None:
+        out = np.zeros((n_barcodes, 2), np.int32) if want_counts else None
+        self._ck(self.lib.hast_finish(self._ctx, _ptr(out), n_barcodes))
+        return out
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self.lib.hast_stats_get(self._ctx, C.byref(s)))
+        return s.as_dict()
+
+    def counts_device_ptr(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.hast_counts_device_ptr(self._ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def timer_start(self):
+        self._ck(self.lib.hast_timer_start(self._ctx))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.hast_timer_stop(self._ctx, C.byref(ms)))
+        return ms.value
+
+    # -- multi-GPU ----------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.hast_comm_unique_id(buf)
+        if rc:
+            raise HastError(rc, (self.lib.hast_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init_rank(self, nranks: int, rank: int, uid: bytes):
+        assert len(uid) == 128
+        self._ck(self.lib.hast_comm_init_rank(self._ctx, nranks, rank, C.create_string_buffer(uid, 128)))
+
+    # -- standalone K2 / K3 ---------------------------------------------------
+    def extract_kmers(self, bases: np.ndarray, read_off: np.ndarray):
+        """Returns (kmers[n_bases] with ~0 where no k-mer starts, has_n[n_reads])."""
+        bases = _arr(bases, np.uint8).reshape(-1)
+        read_off = _arr(read_off, np.uint32)
+        n_reads = read_off.size - 1
+        out = np.empty(bases.size, np.uint64)
+        has_n = np.zeros(n_reads, np.uint8)
+        self._ck(self.lib.hast_extract_kmers(self._ctx, _ptr(bases), bases.size, _ptr(read_off), n_reads,
+                                             _ptr(out), out.size, _ptr(has_n)))
+        return out, has_n
+
+    def lookup(self, canonical: np.ndarray) -> np.ndarray:
+        canonical = _arr(canonical, np.uint64)
+        out = np.zeros(canonical.size, np.uint8)
+        self._ck(self.lib.hast_lookup(self._ctx, _ptr(canonical), canonical.size, _ptr(out)))
+        return out
+
+    def extract_kmers_device(self, bases_ptr, n_bases, off_ptr, n_reads, out_ptr, has_n_ptr=None):
+        self._ck(self.lib.hast_extract_kmers_device(self._ctx, bases_ptr, n_bases, off_ptr, n_reads, out_ptr, has_n_ptr))
+
+    def lookup_device(self, canon_ptr, n, tags_ptr):
+        self._ck(self.lib.hast_lookup_device(self._ctx, canon_ptr, n, tags_ptr))
+
+    def gather_roofline(self, n_probes: int, span_bytes: int) -> float:
+        g = C.c_float()
+        self._ck(self.lib.hast_gather_roofline(self._ctx, int(n_probes), int(span_bytes), C.byref(g)))
+        return g.value

@@ -1,0 +1,726 @@
+// hast_b200.cu -- C ABI (include/hast_b200.h) over the sm_100a kernels.
+//
+// Host-side plumbing only: contexts, streams, the double-buffered H2D ring,
+// launches, the NCCL reduce of the per-barcode counters.  No compute happens
+// on the host and there is no CPU fallback: without a CUDA device every entry
+// point that needs one fails with HAST_E_CUDA.
+#include "../../include/hast_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace hast;
+
+namespace {
+
+constexpr int kSlots = 3;                 // device-side staging ring (double buffering + 1)
+
+struct Slot {
+    uint8_t* d_bases = nullptr;  size_t cap_bases = 0;
+    uint32_t* d_off = nullptr;   size_t cap_off = 0;
+    uint32_t* d_bc = nullptr;    size_t cap_bc = 0;
+    cudaEvent_t copied = nullptr, done = nullptr;
+};
+
+// ---- NCCL through dlopen: a single-GPU run never needs the library ---------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t,
+                           cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+std::string g_global_err;
+
+bool nccl_load() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.ok) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return false;
+#define HAST_SYM(field, name) \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name); \
+    if (!g_nccl.field) return false;
+    HAST_SYM(GetUniqueId, "ncclGetUniqueId")
+    HAST_SYM(CommInitRank, "ncclCommInitRank")
+    HAST_SYM(CommInitAll, "ncclCommInitAll")
+    HAST_SYM(CommDestroy, "ncclCommDestroy")
+    HAST_SYM(Reduce, "ncclReduce")
+    HAST_SYM(GroupStart, "ncclGroupStart")
+    HAST_SYM(GroupEnd, "ncclGroupEnd")
+    HAST_SYM(GetErrorString, "ncclGetErrorString")
+#undef HAST_SYM
+    g_nccl.ok = true;
+    return true;
+}
+
+}  // namespace
+
+struct hast_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t cs = nullptr;            // compute stream
+    cudaStream_t hs = nullptr;            // host-to-device copy stream
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+
+    TableView tv{};
+    uint64_t n_buckets = 0;
+    bool table_ready = false;
+
+    int32_t* d_counts = nullptr;
+    uint64_t n_barcodes = 0, cap_barcodes = 0;
+    int32_t* d_reduced = nullptr;
+    uint64_t cap_reduced = 0;
+
+    DevStats* d_stats = nullptr;
+    Slot slot[kSlots];
+    uint64_t seq = 0;
+    hast_stats st{};
+
+    void* d_scratch = nullptr;
+    size_t cap_scratch = 0;
+
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+
+    int tile_blocks = 0;                  // persistent grid of the tile kernels
+    std::string err;
+};
+
+namespace {
+
+int fail(hast_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_global_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(ctx, HAST_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+#define NC(call)                                                                                 \
+    do {                                                                                         \
+        ncclResult_t r_ = (call);                                                                \
+        if (r_ != ncclSuccess)                                                                   \
+            return fail(ctx, HAST_E_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+int grid_for(const hast_ctx* c, uint64_t n, int threads, int per_sm = 8) {
+    uint64_t want = (n + threads - 1) / threads;
+    uint64_t cap = (uint64_t)c->sm_count * per_sm;
+    return (int)std::max<uint64_t>(1, std::min(want, cap));
+}
+
+int ensure(hast_ctx* ctx, void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes && *p) return HAST_OK;
+    if (*p) { CU(cudaStreamSynchronize(ctx->cs)); CU(cudaStreamSynchronize(ctx->hs)); CU(cudaFree(*p)); *p = nullptr; }
+    size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 16);
+    CU(cudaMalloc(p, want));
+    *cap = want;
+    return HAST_OK;
+}
+
+int read_stats(hast_ctx* ctx, DevStats* out) {
+    CU(cudaMemcpyAsync(out, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->cs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    return HAST_OK;
+}
+
+int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv, uint64_t* d_kmers, uint8_t* d_has_n) {
+    const uint32_t n_tiles = (bv.n_reads + kReadsPerTile - 1) / kReadsPerTile;
+    if (!n_tiles) return HAST_OK;
+    const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->tile_blocks);
+    if (mode == MODE_CLASSIFY)
+        tile_kernel<MODE_CLASSIFY><<<grid, kTileThreads, 0, ctx->cs>>>(
+            ctx->tv, bv, ctx->d_counts, (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull),
+            ctx->d_stats, nullptr, nullptr);
+    else
+        tile_kernel<MODE_EXTRACT><<<grid, kTileThreads, 0, ctx->cs>>>(ctx->tv, bv, nullptr, 0, ctx->d_stats,
+                                                                     d_kmers, d_has_n);
+    CU(cudaGetLastError());
+    ctx->st.kernel_launches++;
+    return HAST_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hast_abi_version(void) { return HAST_ABI_VERSION; }
+
+int hast_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* hast_last_error(const hast_ctx* ctx) { return ctx ? ctx->err.c_str() : g_global_err.c_str(); }
+int hast_device(const hast_ctx* ctx) { return ctx ? ctx->device : -1; }
+
+int hast_create(int device, hast_ctx** out) {
+    hast_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, HAST_E_ARG, "hast_create: out is NULL");
+    *out = nullptr;
+    int n = hast_device_count();
+    if (n <= 0) return fail(nullptr, HAST_E_CUDA, "no CUDA device: this library has no CPU path");
+    if (device < 0 || device >= n) return fail(nullptr, HAST_E_ARG, "hast_create: bad device index");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, HAST_E_CUDA, "device is not sm_100-class (built for sm_100a only)");
+    ctx = new hast_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e;
+#define CU_NEW(call) if ((e = (call)) != cudaSuccess) { g_global_err = std::string(#call) + ": " + cudaGetErrorString(e); delete ctx; return HAST_E_CUDA; }
+    CU_NEW(cudaStreamCreateWithFlags(&ctx->cs, cudaStreamNonBlocking));
+    CU_NEW(cudaStreamCreateWithFlags(&ctx->hs, cudaStreamNonBlocking));
+    CU_NEW(cudaEventCreate(&ctx->t0));
+    CU_NEW(cudaEventCreate(&ctx->t1));
+    for (auto& s : ctx->slot) {
+        CU_NEW(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+        CU_NEW(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    CU_NEW(cudaMalloc(&ctx->d_stats, sizeof(DevStats)));
+    CU_NEW(cudaMemset(ctx->d_stats, 0, sizeof(DevStats)));
+    int per_sm = 0;
+    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel<MODE_CLASSIFY>, kTileThreads, 0));
+#undef CU_NEW
+    ctx->tile_blocks = std::max(1, per_sm) * ctx->sm_count;
+    *out = ctx;
+    return HAST_OK;
+}
+
+void hast_destroy(hast_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    for (auto& s : ctx->slot) {
+        cudaFree(s.d_bases); cudaFree(s.d_off); cudaFree(s.d_bc);
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    cudaFree(ctx->tv.slots);
+    cudaFree(ctx->d_counts);
+    cudaFree(ctx->d_reduced);
+    cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_scratch);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->cs) cudaStreamDestroy(ctx->cs);
+    if (ctx->hs) cudaStreamDestroy(ctx->hs);
+    delete ctx;
+}
+
+int hast_host_alloc(void** ptr, size_t bytes) {
+    hast_ctx* ctx = nullptr;
+    if (!ptr) return fail(nullptr, HAST_E_ARG, "hast_host_alloc: ptr is NULL");
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return HAST_OK;
+}
+int hast_host_free(void* ptr) {
+    hast_ctx* ctx = nullptr;
+    if (ptr) CU(cudaFreeHost(ptr));
+    return HAST_OK;
+}
+
+// ---- K1 ------------------------------------------------------------------
+int hast_table_begin(hast_ctx* ctx, int k, uint64_t expected_keys) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (k < 1 || k > 32) return fail(ctx, HAST_E_K, "k must be in 1..32 (reference is only correct for k <= 32, kmer.h:225-238)");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->cs));
+    if (ctx->tv.slots) { CU(cudaFree(ctx->tv.slots)); ctx->tv.slots = nullptr; }
+    ctx->table_ready = false;
+    // load factor <= 0.5 over 4-slot buckets => at least expected/2 buckets, power of two
+    int b = 4;
+    while (((uint64_t)1 << b) * 2 < expected_keys && b < 40) ++b;
+    const int bmin = std::max(0, 2 * k - 57);          // rem must fit the slot
+    const int bmax = 2 * k;                            // bucket index comes out of the 2k-bit hash
+    b = std::max(b, bmin);
+    b = std::min(b, bmax);
+    if (b > 32) return fail(ctx, HAST_E_ARG, "table too large");
+    ctx->n_buckets = (uint64_t)1 << b;
+    const size_t bytes = ctx->n_buckets * kSlotsPerBucket * sizeof(uint64_t);
+    CU(cudaMalloc(&ctx->tv.slots, bytes));
+    CU(cudaMemsetAsync(ctx->tv.slots, 0, bytes, ctx->cs));
+    ctx->tv.k = k;
+    ctx->tv.kmask = kmer_mask(k);
+    ctx->tv.rem_bits = 2 * k - b;
+    ctx->tv.rem_mask = ctx->tv.rem_bits ? (((uint64_t)1 << ctx->tv.rem_bits) - 1) : 0;
+    ctx->tv.bucket_mask = (uint32_t)(ctx->n_buckets - 1);
+    CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->cs));
+    if (ctx->d_counts) CU(cudaMemsetAsync(ctx->d_counts, 0, ctx->cap_barcodes * 2 * sizeof(int32_t), ctx->cs));
+    ctx->table_ready = true;
+    return HAST_OK;
+}
+
+static int table_check(hast_ctx* ctx) {
+    DevStats ds;
+    int rc = read_stats(ctx, &ds);
+    if (rc) return rc;
+    if (ds.bad_kmer_lines)
+        return fail(ctx, HAST_E_KMER_LINE, std::to_string(ds.bad_kmer_lines) +
+                    " k-mer line(s) whose length differs from k=" + std::to_string(ctx->tv.k));
+    if (ds.table_full)
+        return fail(ctx, HAST_E_TABLE_FULL, std::to_string(ds.table_full) +
+                    " k-mer(s) could not be placed: rebuild with a larger expected_keys");
+    return HAST_OK;
+}
+
+int hast_table_add_text(hast_ctx* ctx, const char* text, uint64_t n_lines, int parent) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (!ctx->table_ready) return fail(ctx, HAST_E_STATE, "hast_table_begin first");
+    if (parent < 0 || parent > 1) return fail(ctx, HAST_E_ARG, "parent must be 0 or 1");
+    if (!n_lines) return HAST_OK;
+    if (!text) return fail(ctx, HAST_E_ARG, "text is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t stride = (uint64_t)ctx->tv.k + 1;
+    const uint64_t chunk_lines = std::max<uint64_t>(1, ((uint64_t)256 << 20) / stride);
+    for (uint64_t done = 0; done < n_lines; done += chunk_lines) {
+        const uint64_t n = std::min(chunk_lines, n_lines - done);
+        int rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, n * stride);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ctx->d_scratch, text + done * stride, n * stride, cudaMemcpyHostToDevice, ctx->cs));
+        ctx->st.h2d_bytes += n * stride;
+        table_insert_text_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->cs>>>(
+            ctx->tv, (const char*)ctx->d_scratch, n, (uint32_t)parent, ctx->d_stats);
+        CU(cudaGetLastError());
+        ctx->st.kernel_launches++;
+        CU(cudaStreamSynchronize(ctx->cs));        // the scratch buffer is reused by the next chunk
+    }
+    return table_check(ctx);
+}
+
+int hast_table_add_packed(hast_ctx* ctx, const uint64_t* kmers, uint64_t n, int parent) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (!ctx->table_ready) return fail(ctx, HAST_E_STATE, "hast_table_begin first");
+    if (parent < 0 || parent > 1) return fail(ctx, HAST_E_ARG, "parent must be 0 or 1");
+    if (!n) return HAST_OK;
+    if (!kmers) return fail(ctx, HAST_E_ARG, "kmers is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t chunk = (uint64_t)32 << 20;
+    for (uint64_t done = 0; done < n; done += chunk) {
+        const uint64_t m = std::min(chunk, n - done);
+        int rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, m * 8);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ctx->d_scratch, kmers + done, m * 8, cudaMemcpyHostToDevice, ctx->cs));
+        ctx->st.h2d_bytes += m * 8;
+        table_insert_packed_kernel<<<grid_for(ctx, m, 256), 256, 0, ctx->cs>>>(
+            ctx->tv, (const uint64_t*)ctx->d_scratch, m, (uint32_t)parent, ctx->d_stats);
+        CU(cudaGetLastError());
+        ctx->st.kernel_launches++;
+        CU(cudaStreamSynchronize(ctx->cs));
+    }
+    return table_check(ctx);
+}
+
+int hast_table_erase_seq(hast_ctx* ctx, const char* seq, uint32_t len, uint64_t* erased_out,
+                         uint8_t* tags_out, uint32_t cap, uint32_t* n_erased) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (!ctx->table_ready) return fail(ctx, HAST_E_STATE, "hast_table_begin first");
+    if (!seq) return fail(ctx, HAST_E_ARG, "seq is NULL");
+    if (len < (uint32_t)ctx->tv.k)                      // chopRead2Kmer assert, kmer.h:171
+        return fail(ctx, HAST_E_SHORT_READ, "adaptor shorter than k");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t nk = len - (uint32_t)ctx->tv.k + 1;
+    const size_t o_seq = 0, o_er = (len + 15) & ~(size_t)15, o_tag = o_er + (size_t)nk * 8,
+                 o_n = (o_tag + nk + 15) & ~(size_t)15, total = o_n + 16;
+    int rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, total);
+    if (rc) return rc;
+    char* d = (char*)ctx->d_scratch;
+    CU(cudaMemcpyAsync(d + o_seq, seq, len, cudaMemcpyHostToDevice, ctx->cs));
+    table_erase_kernel<<<1, 32, 0, ctx->cs>>>(ctx->tv, d + o_seq, len, (uint64_t*)(d + o_er),
+                                              (uint8_t*)(d + o_tag), nk, (uint32_t*)(d + o_n));
+    CU(cudaGetLastError());
+    ctx->st.kernel_launches++;
+    uint32_t n = 0;
+    CU(cudaMemcpyAsync(&n, d + o_n, 4, cudaMemcpyDeviceToHost, ctx->cs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    const uint32_t m = std::min(n, cap);
+    if (m && erased_out) CU(cudaMemcpy(erased_out, d + o_er, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    if (m && tags_out) CU(cudaMemcpy(tags_out, d + o_tag, m, cudaMemcpyDeviceToHost));
+    if (n_erased) *n_erased = n;
+    return HAST_OK;
+}
+
+int hast_table_info_get(hast_ctx* ctx, hast_table_info* out) {
+    if (!ctx || !out) return fail(ctx, HAST_E_ARG, "NULL argument");
+    if (!ctx->table_ready) return fail(ctx, HAST_E_STATE, "hast_table_begin first");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, sizeof(TableCounts));
+    if (rc) return rc;
+    CU(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(TableCounts), ctx->cs));
+    table_count_kernel<<<grid_for(ctx, ctx->n_buckets, 256), 256, 0, ctx->cs>>>(
+        ctx->tv.slots, ctx->n_buckets, (TableCounts*)ctx->d_scratch);
+    CU(cudaGetLastError());
+    ctx->st.kernel_launches++;
+    TableCounts tc;
+    CU(cudaMemcpyAsync(&tc, ctx->d_scratch, sizeof(tc), cudaMemcpyDeviceToHost, ctx->cs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    out->k = ctx->tv.k;
+    out->log2_buckets = 2 * ctx->tv.k - ctx->tv.rem_bits;
+    out->n_buckets = ctx->n_buckets;
+    out->bytes = ctx->n_buckets * kSlotsPerBucket * 8;
+    out->n_entries = tc.entries;
+    out->n_displaced = tc.displaced;
+    out->n_overflow_buckets = tc.overflow_buckets;
+    out->size[0] = tc.size0;
+    out->size[1] = tc.size1;
+    return HAST_OK;
+}
+
+int hast_table_clone(hast_ctx* dst, hast_ctx* src) {
+    hast_ctx* ctx = dst;
+    if (!dst || !src) return fail(dst, HAST_E_ARG, "NULL context");
+    if (!src->table_ready) return fail(dst, HAST_E_STATE, "source table not built");
+    CU(cudaSetDevice(src->device));
+    CU(cudaStreamSynchronize(src->cs));
+    CU(cudaSetDevice(dst->device));
+    CU(cudaStreamSynchronize(dst->cs));
+    if (dst->tv.slots) { CU(cudaFree(dst->tv.slots)); dst->tv.slots = nullptr; }
+    const size_t bytes = src->n_buckets * kSlotsPerBucket * 8;
+    uint64_t* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    CU(cudaMemcpyPeer(p, dst->device, src->tv.slots, src->device, bytes));
+    dst->tv = src->tv;
+    dst->tv.slots = p;
+    dst->n_buckets = src->n_buckets;
+    dst->table_ready = true;
+    return HAST_OK;
+}
+
+// ---- K4 state ------------------------------------------------------------
+int hast_reserve_barcodes(hast_ctx* ctx, uint64_t n) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (n > 0xFFFFFFFFull) return fail(ctx, HAST_E_ARG, "more than 2^32 barcodes");
+    CU(cudaSetDevice(ctx->device));
+    if (n > ctx->cap_barcodes) {
+        const uint64_t cap = std::max<uint64_t>(n + n / 2, 1024);
+        int32_t* p = nullptr;
+        CU(cudaMalloc(&p, cap * 2 * sizeof(int32_t)));
+        CU(cudaMemsetAsync(p, 0, cap * 2 * sizeof(int32_t), ctx->cs));
+        if (ctx->d_counts) {
+            CU(cudaMemcpyAsync(p, ctx->d_counts, ctx->cap_barcodes * 2 * sizeof(int32_t),
+                               cudaMemcpyDeviceToDevice, ctx->cs));
+            CU(cudaStreamSynchronize(ctx->cs));
+            CU(cudaFree(ctx->d_counts));
+        }
+        ctx->d_counts = p;
+        ctx->cap_barcodes = cap;
+    }
+    ctx->n_barcodes = std::max(ctx->n_barcodes, n);
+    return HAST_OK;
+}
+
+int hast_reset_counts(hast_ctx* ctx) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->d_counts) CU(cudaMemsetAsync(ctx->d_counts, 0, ctx->cap_barcodes * 2 * sizeof(int32_t), ctx->cs));
+    CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->cs));
+    memset(&ctx->st, 0, sizeof(ctx->st));
+    return HAST_OK;
+}
+
+// ---- batches ---------------------------------------------------------------
+static int batch_args_ok(hast_ctx* ctx, const void* bases, const void* off, const void* bc, uint64_t n_bases,
+                         uint32_t n_reads) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (!ctx->table_ready) return fail(ctx, HAST_E_STATE, "no table: hast_table_begin/add first");
+    if (n_reads && (!off || !bc || (!bases && n_bases))) return fail(ctx, HAST_E_ARG, "NULL batch array");
+    if (n_bases >= 0xFFFFFFF0ull) return fail(ctx, HAST_E_ARG, "batch larger than 4 GiB of bases");
+    if (!ctx->d_counts) return fail(ctx, HAST_E_STATE, "hast_reserve_barcodes first");
+    return HAST_OK;
+}
+
+int hast_submit_batch(hast_ctx* ctx, const uint8_t* bases, uint64_t n_bases, const uint32_t* read_off,
+                      const uint32_t* barcode_id, uint32_t n_reads, uint64_t* ticket) {
+    int rc = batch_args_ok(ctx, bases, read_off, barcode_id, n_bases, n_reads);
+    if (rc) return rc;
+    if (ticket) *ticket = ctx->seq;
+    if (!n_reads) return HAST_OK;
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[ctx->seq % kSlots];
+    CU(cudaEventSynchronize(s.done));                   // the kernel that last used this slot
+    if ((rc = ensure(ctx, (void**)&s.d_bases, &s.cap_bases, n_bases + 16))) return rc;
+    if ((rc = ensure(ctx, (void**)&s.d_off, &s.cap_off, ((size_t)n_reads + 1) * 4))) return rc;
+    if ((rc = ensure(ctx, (void**)&s.d_bc, &s.cap_bc, (size_t)n_reads * 4))) return rc;
+    CU(cudaMemcpyAsync(s.d_bases, bases, n_bases, cudaMemcpyHostToDevice, ctx->hs));
+    CU(cudaMemcpyAsync(s.d_off, read_off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, ctx->hs));
+    CU(cudaMemcpyAsync(s.d_bc, barcode_id, (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->hs));
+    CU(cudaEventRecord(s.copied, ctx->hs));
+    CU(cudaStreamWaitEvent(ctx->cs, s.copied, 0));
+    BatchView bv{s.d_bases, s.d_off, s.d_bc, n_bases, n_reads};
+    if ((rc = launch_tile(ctx, MODE_CLASSIFY, bv, nullptr, nullptr))) return rc;
+    CU(cudaEventRecord(s.done, ctx->cs));
+    ctx->st.h2d_bytes += n_bases + ((size_t)n_reads + 1) * 4 + (size_t)n_reads * 4;
+    ctx->st.batches++;
+    ctx->st.reads += n_reads;
+    ctx->st.bases += n_bases;
+    ctx->seq++;
+    return HAST_OK;
+}
+
+int hast_wait_copied(hast_ctx* ctx, uint64_t ticket) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (ticket >= ctx->seq) return HAST_OK;             // empty batch or nothing submitted
+    if (ctx->seq - ticket > kSlots) return HAST_OK;     // slot already recycled => copy long done
+    CU(cudaEventSynchronize(ctx->slot[ticket % kSlots].copied));
+    return HAST_OK;
+}
+
+int hast_submit_batch_device(hast_ctx* ctx, const uint8_t* d_bases, uint64_t n_bases,
+                             const uint32_t* d_read_off, const uint32_t* d_barcode_id, uint32_t n_reads) {
+    int rc = batch_args_ok(ctx, d_bases, d_read_off, d_barcode_id, n_bases, n_reads);
+    if (rc) return rc;
+    if (!n_reads) return HAST_OK;
+    if ((uintptr_t)d_bases & 15) return fail(ctx, HAST_E_ARG, "d_bases must be 16-byte aligned");
+    CU(cudaSetDevice(ctx->device));
+    BatchView bv{d_bases, d_read_off, d_barcode_id, n_bases, n_reads};
+    if ((rc = launch_tile(ctx, MODE_CLASSIFY, bv, nullptr, nullptr))) return rc;
+    ctx->st.batches++;
+    ctx->st.reads += n_reads;
+    ctx->st.bases += n_bases;
+    return HAST_OK;
+}
+
+int hast_sync(hast_ctx* ctx) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->hs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    return HAST_OK;
+}
+
+int hast_stats_get(hast_ctx* ctx, hast_stats* out) {
+    if (!ctx || !out) return fail(ctx, HAST_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    DevStats ds;
+    int rc = read_stats(ctx, &ds);
+    if (rc) return rc;
+    *out = ctx->st;
+    out->lookups = ds.lookups;
+    out->reads_with_n = ds.reads_with_n;
+    out->reads_short = ds.reads_short;
+    out->extra_probes = ds.extra_probes;
+    return HAST_OK;
+}
+
+int hast_counts_device_ptr(hast_ctx* ctx, void** ptr, uint64_t* n_barcodes) {
+    if (!ctx || !ptr) return fail(ctx, HAST_E_ARG, "NULL argument");
+    *ptr = ctx->d_counts;
+    if (n_barcodes) *n_barcodes = ctx->n_barcodes;
+    return HAST_OK;
+}
+
+int hast_timer_start(hast_ctx* ctx) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->t0, ctx->cs));
+    return HAST_OK;
+}
+int hast_timer_stop(hast_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(ctx, HAST_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->t1, ctx->cs));
+    CU(cudaEventSynchronize(ctx->t1));
+    CU(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return HAST_OK;
+}
+
+int hast_finish(hast_ctx* ctx, int32_t* counts_out, uint64_t n_barcodes) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->hs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    DevStats ds;
+    int rc = read_stats(ctx, &ds);
+    if (rc) return rc;
+    if (ds.reads_short)
+        return fail(ctx, HAST_E_SHORT_READ, std::to_string(ds.reads_short) + " read(s) shorter than k=" +
+                    std::to_string(ctx->tv.k) + " (the reference aborts on these, kmer.h:171)");
+    if (ds.reads_too_long)
+        return fail(ctx, HAST_E_ARG, std::to_string(ds.reads_too_long) + " read(s) longer than " +
+                    std::to_string(kTileCapBytes - 16) + " bases");
+    if (ds.bad_barcode)
+        return fail(ctx, HAST_E_ARG, std::to_string(ds.bad_barcode) + " read(s) with barcode id >= reserved barcodes");
+    if (n_barcodes > ctx->n_barcodes) return fail(ctx, HAST_E_ARG, "n_barcodes exceeds reserved barcodes");
+    const int32_t* src = ctx->d_counts;
+    if (ctx->comm) {
+        if (n_barcodes > ctx->cap_reduced) {
+            if (ctx->d_reduced) CU(cudaFree(ctx->d_reduced));
+            CU(cudaMalloc(&ctx->d_reduced, std::max<uint64_t>(n_barcodes, 1) * 2 * sizeof(int32_t)));
+            ctx->cap_reduced = n_barcodes;
+        }
+        // BarcodeCache::Add (classify.cpp:57-63) across GPUs: one int32 sum to rank 0
+        NC(g_nccl.Reduce(ctx->d_counts, ctx->d_reduced, n_barcodes * 2, ncclInt32, ncclSum, 0, ctx->comm, ctx->cs));
+        CU(cudaStreamSynchronize(ctx->cs));
+        src = ctx->d_reduced;
+    }
+    if (counts_out && n_barcodes && ctx->rank == 0) {
+        CU(cudaMemcpyAsync(counts_out, src, n_barcodes * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cs));
+        CU(cudaStreamSynchronize(ctx->cs));
+        ctx->st.d2h_bytes += n_barcodes * 2 * sizeof(int32_t);
+    }
+    return HAST_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------
+int hast_comm_unique_id(void* id128) {
+    hast_ctx* ctx = nullptr;
+    if (!id128) return fail(nullptr, HAST_E_ARG, "NULL id");
+    if (!nccl_load()) return fail(nullptr, HAST_E_NCCL, "libnccl.so.2 not loadable");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return HAST_OK;
+}
+
+int hast_comm_init_rank(hast_ctx* ctx, int nranks, int rank, const void* id128) {
+    if (!ctx || !id128) return fail(ctx, HAST_E_ARG, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, HAST_E_ARG, "bad rank / nranks");
+    if (!nccl_load()) return fail(ctx, HAST_E_NCCL, "libnccl.so.2 not loadable");
+    CU(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NC(g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return HAST_OK;
+}
+
+int hast_comm_init_all(hast_ctx** ctxs, int n) {
+    hast_ctx* ctx = (ctxs && n > 0) ? ctxs[0] : nullptr;
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "no contexts");
+    if (n == 1) return HAST_OK;
+    if (!nccl_load()) return fail(ctx, HAST_E_NCCL, "libnccl.so.2 not loadable");
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n);
+    for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
+    NC(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; ++i) { ctxs[i]->comm = comms[i]; ctxs[i]->nranks = n; ctxs[i]->rank = i; }
+    return HAST_OK;
+}
+
+// ---- standalone K2 / K3 ----------------------------------------------------
+int hast_extract_kmers_device(hast_ctx* ctx, const uint8_t* d_bases, uint64_t n_bases,
+                              const uint32_t* d_read_off, uint32_t n_reads, uint64_t* d_kmers_out,
+                              uint8_t* d_has_n_out) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (!ctx->table_ready) return fail(ctx, HAST_E_STATE, "hast_table_begin first (fixes k)");
+    if (!n_reads) return HAST_OK;
+    if (!d_bases || !d_read_off || !d_kmers_out) return fail(ctx, HAST_E_ARG, "NULL array");
+    if ((uintptr_t)d_bases & 15) return fail(ctx, HAST_E_ARG, "d_bases must be 16-byte aligned");
+    if (n_bases >= 0xFFFFFFF0ull) return fail(ctx, HAST_E_ARG, "batch larger than 4 GiB of bases");
+    CU(cudaSetDevice(ctx->device));
+    BatchView bv{d_bases, d_read_off, nullptr, n_bases, n_reads};
+    return launch_tile(ctx, MODE_EXTRACT, bv, d_kmers_out, d_has_n_out);
+}
+
+int hast_extract_kmers(hast_ctx* ctx, const uint8_t* bases, uint64_t n_bases, const uint32_t* read_off,
+                       uint32_t n_reads, uint64_t* kmers_out, uint64_t n_kmers_out, uint8_t* has_n_out) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (!ctx->table_ready) return fail(ctx, HAST_E_STATE, "hast_table_begin first (fixes k)");
+    if (!n_reads) return HAST_OK;
+    if (!bases || !read_off || !kmers_out) return fail(ctx, HAST_E_ARG, "NULL array");
+    if (n_kmers_out < n_bases) return fail(ctx, HAST_E_ARG, "kmers_out needs one slot per base position");
+    CU(cudaSetDevice(ctx->device));
+    const size_t o_b = 0, o_off = (n_bases + 16 + 15) & ~(size_t)15, o_n = o_off + (((size_t)n_reads + 1) * 4 + 15 & ~(size_t)15),
+                 o_k = (o_n + n_reads + 15) & ~(size_t)15, total = o_k + n_bases * 8;
+    int rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, total);
+    if (rc) return rc;
+    char* d = (char*)ctx->d_scratch;
+    CU(cudaMemcpyAsync(d + o_b, bases, n_bases, cudaMemcpyHostToDevice, ctx->cs));
+    CU(cudaMemcpyAsync(d + o_off, read_off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, ctx->cs));
+    CU(cudaMemsetAsync(d + o_k, 0xFF, n_bases * 8, ctx->cs));   // positions that start no k-mer
+    rc = hast_extract_kmers_device(ctx, (const uint8_t*)(d + o_b), n_bases, (const uint32_t*)(d + o_off), n_reads,
+                                   (uint64_t*)(d + o_k), (uint8_t*)(d + o_n));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(kmers_out, d + o_k, n_bases * 8, cudaMemcpyDeviceToHost, ctx->cs));
+    if (has_n_out) CU(cudaMemcpyAsync(has_n_out, d + o_n, n_reads, cudaMemcpyDeviceToHost, ctx->cs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    return HAST_OK;
+}
+
+int hast_lookup_device(hast_ctx* ctx, const uint64_t* d_canonical, uint64_t n, uint8_t* d_tags_out) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (!ctx->table_ready) return fail(ctx, HAST_E_STATE, "no table");
+    if (!n) return HAST_OK;
+    if (!d_canonical || !d_tags_out) return fail(ctx, HAST_E_ARG, "NULL array");
+    CU(cudaSetDevice(ctx->device));
+    lookup_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->cs>>>(ctx->tv, d_canonical, n, d_tags_out, ctx->d_stats);
+    CU(cudaGetLastError());
+    ctx->st.kernel_launches++;
+    return HAST_OK;
+}
+
+int hast_lookup(hast_ctx* ctx, const uint64_t* canonical, uint64_t n, uint8_t* tags_out) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (!ctx->table_ready) return fail(ctx, HAST_E_STATE, "no table");
+    if (!n) return HAST_OK;
+    if (!canonical || !tags_out) return fail(ctx, HAST_E_ARG, "NULL array");
+    CU(cudaSetDevice(ctx->device));
+    const size_t o_t = n * 8;
+    int rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, o_t + n);
+    if (rc) return rc;
+    char* d = (char*)ctx->d_scratch;
+    CU(cudaMemcpyAsync(d, canonical, n * 8, cudaMemcpyHostToDevice, ctx->cs));
+    rc = hast_lookup_device(ctx, (const uint64_t*)d, n, (uint8_t*)(d + o_t));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(tags_out, d + o_t, n, cudaMemcpyDeviceToHost, ctx->cs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    return HAST_OK;
+}
+
+int hast_gather_roofline(hast_ctx* ctx, uint64_t n_probes, uint64_t span_bytes, float* gbps) {
+    if (!ctx || !gbps) return fail(ctx, HAST_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    uint64_t sectors = 1;
+    while (sectors * 2 * 32 <= span_bytes) sectors *= 2;
+    const size_t bytes = sectors * 32;
+    int rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, bytes + 64);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(ctx->d_scratch, 0x5A, bytes, ctx->cs));
+    unsigned long long* sink = (unsigned long long*)((char*)ctx->d_scratch + bytes);
+    const int grid = ctx->sm_count * 8;
+    gather_kernel<<<grid, 256, 0, ctx->cs>>>((const uint64_t*)ctx->d_scratch, sectors - 1, n_probes / 8, sink);  // warm-up
+    CU(cudaEventRecord(ctx->t0, ctx->cs));
+    gather_kernel<<<grid, 256, 0, ctx->cs>>>((const uint64_t*)ctx->d_scratch, sectors - 1, n_probes, sink);
+    CU(cudaEventRecord(ctx->t1, ctx->cs));
+    CU(cudaGetLastError());
+    CU(cudaEventSynchronize(ctx->t1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->t0, ctx->t1));
+    ctx->st.kernel_launches += 2;
+    *gbps = ms > 0 ? (float)((double)n_probes * 32.0 / (ms * 1e-3) / 1e9) : 0.f;
+    return HAST_OK;
+}
+
+}  // extern "C"

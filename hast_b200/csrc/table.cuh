@@ -1,0 +1,102 @@
+// table.cuh -- the parent-unique k-mer table (replaces the two
+// std::unordered_set<Kmer> of classify.cpp:27).
+//
+// Layout in HBM: 2^b buckets of 32 bytes (= one DRAM/L2 sector), four 8-byte
+// slots per bucket, so a lookup -- hit or miss -- costs ONE 32-byte sector read
+// (a single LDG.E.256 on sm_100a) unless its home bucket overflowed.
+//
+//   h      = bijective mix of the canonical k-mer inside the 2k-bit domain
+//   bucket = top b bits of h          (home bucket)
+//   rem    = low 2k-b bits of h       (quotient: with the home bucket it
+//                                      identifies the k-mer exactly, which is
+//                                      what makes room for k = 32)
+//   slot   = rem << 7 | disp << 3 | tag << 1 | ovf
+//              disp : 0..15, distance (in buckets) from the home bucket
+//              tag  : bit0 = member of hap0 set, bit1 = member of hap1 set
+//                     (a k-mer may be in both: classify.cpp:195-202 scores the
+//                     two sets independently); tag 0 = empty or erased
+//              ovf  : meaningful in slot 0 only: some insertion passed through
+//                     this full bucket, so a miss must look at the next one
+//
+// An all-zero slot is empty; it can only compare equal to (rem 0, disp 0) and
+// then yields tag 0, which is the correct answer for an absent k-mer.
+#pragma once
+#include <cstdint>
+#include "kmer.cuh"
+
+namespace hast {
+
+constexpr int kSlotsPerBucket = 4;
+constexpr int kMaxDisp = 15;
+constexpr int kRemShift = 7;
+constexpr uint64_t kHashC1 = 0x9E3779B97F4A7C15ull;
+constexpr uint64_t kHashC2 = 0xD6E8FEB86659FD93ull;
+
+struct TableView {
+    uint64_t* slots;        // n_buckets * 4
+    uint64_t kmask;         // 2k low bits
+    uint64_t rem_mask;      // (1 << rem_bits) - 1
+    uint32_t bucket_mask;   // n_buckets - 1
+    int32_t k;
+    int32_t rem_bits;       // 2k - b, 0..57
+};
+
+// multiply / xor-shift / multiply, every step a bijection of Z/2^(2k)
+__host__ __device__ __forceinline__ uint64_t table_hash(uint64_t key, int k, uint64_t kmask) {
+    uint64_t h = (key * kHashC1) & kmask;
+    h ^= h >> k;
+    h = (h * kHashC2) & kmask;
+    return h;
+}
+
+#ifdef __CUDACC__
+struct Bucket { uint64_t s0, s1, s2, s3; };
+
+// one 32-byte sector, read-only path, no L1 allocation (no reuse inside an SM)
+__device__ __forceinline__ Bucket load_bucket(const uint64_t* p) {
+    Bucket b;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(b.s0), "=l"(b.s1), "=l"(b.s2), "=l"(b.s3) : "l"(p));
+    return b;
+}
+// coherent variant for the build / erase kernels (slots change under them)
+__device__ __forceinline__ Bucket load_bucket_volatile(const uint64_t* p) {
+    Bucket b;
+    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(b.s0), "=l"(b.s1) : "l"(p));
+    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(b.s2), "=l"(b.s3) : "l"(p + 2));
+    return b;
+}
+
+// tag bits of the slot matching `want` (= rem << 4 | disp), 0 if none
+__device__ __forceinline__ uint32_t match_bucket(const Bucket& b, uint64_t want, bool& found) {
+    const bool m0 = (b.s0 >> 3) == want, m1 = (b.s1 >> 3) == want;
+    const bool m2 = (b.s2 >> 3) == want, m3 = (b.s3 >> 3) == want;
+    found = m0 | m1 | m2 | m3;
+    const uint32_t lo = m0 ? (uint32_t)b.s0 : m1 ? (uint32_t)b.s1 : m2 ? (uint32_t)b.s2 : m3 ? (uint32_t)b.s3 : 0u;
+    return (lo >> 1) & 3u;
+}
+
+// g_kmers[0].find / g_kmers[1].find (classify.cpp:195-202) in one probe.
+// `extra` counts bucket reads beyond the first.
+__device__ __forceinline__ uint32_t table_probe(const TableView& t, uint64_t canon, uint32_t& extra) {
+    const uint64_t h = table_hash(canon, t.k, t.kmask);
+    uint32_t bucket = (uint32_t)(h >> t.rem_bits);
+    uint64_t want = (h & t.rem_mask) << 4;
+    Bucket b = load_bucket(t.slots + (size_t)bucket * kSlotsPerBucket);
+    bool found;
+    uint32_t tag = match_bucket(b, want, found);
+    if (!found && (b.s0 & 1ull)) {                       // rare: home bucket overflowed
+        for (int d = 1; d <= kMaxDisp; ++d) {
+            bucket = (bucket + 1) & t.bucket_mask;
+            want += 1;
+            b = load_bucket(t.slots + (size_t)bucket * kSlotsPerBucket);
+            ++extra;
+            tag = match_bucket(b, want, found);
+            if (found || !(b.s0 & 1ull)) break;
+        }
+    }
+    return tag;
+}
+#endif
+
+}  // namespace hast

@@ -1,0 +1,180 @@
+/*
+ * hast_b200.h -- C ABI of the B200 read-classification engine (libhast_b200.so)
+ *
+ * The reference (BGI-Qingdao/HAST, 01.classify_stlfr_reads) has no plugin or
+ * FFI interface: `classify` is one C++ translation unit.  This ABI cuts that
+ * program along its own function boundaries; every entry point names the
+ * reference code it replaces (paths relative to 01.classify_stlfr_reads/).
+ * bin/classify (hast_b200/host/) is the drop-in process built on top of it.
+ *
+ * Conventions
+ *   - plain C: opaque context, plain pointers and sizes, no C++/torch types.
+ *   - every call returns 0 on success or a negative HAST_E_* code; the text of
+ *     the last error is available from hast_last_error().
+ *   - one context per GPU; a context is driven by one host thread at a time.
+ *   - "host" pointers may be pageable or pinned (hast_host_alloc); copies from
+ *     pinned memory are asynchronous and double-buffered on the device side.
+ *   - there is NO CPU implementation behind this interface: without a CUDA
+ *     device every compute entry point fails with HAST_E_CUDA.
+ */
+#ifndef HAST_B200_H
+#define HAST_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HAST_ABI_VERSION 1
+
+#define HAST_OK            0
+#define HAST_E_ARG        -1   /* bad argument                                            */
+#define HAST_E_CUDA       -2   /* CUDA runtime / driver failure, or no device             */
+#define HAST_E_STATE      -3   /* call out of order (e.g. lookup before table build)      */
+#define HAST_E_KMER_LINE  -4   /* k-mer list line whose length != k  (kmer.h:154 assert)  */
+#define HAST_E_SHORT_READ -5   /* read shorter than k                (kmer.h:171 assert)  */
+#define HAST_E_TABLE_FULL -6   /* table capacity exceeded: rebuild with a larger one      */
+#define HAST_E_NCCL       -7   /* NCCL unavailable or failed                              */
+#define HAST_E_K          -8   /* k outside 1..32                                         */
+
+typedef struct hast_ctx hast_ctx;
+
+typedef struct hast_table_info {
+    int32_t  k;
+    int32_t  log2_buckets;
+    uint64_t n_buckets;        /* 32-byte buckets of four 8-byte slots                    */
+    uint64_t bytes;
+    uint64_t n_entries;        /* distinct canonical k-mers stored (either parent)        */
+    uint64_t n_displaced;      /* entries that live outside their home bucket             */
+    uint64_t n_overflow_buckets;
+    uint64_t size[2];          /* g_kmers[i].size() after erases                          */
+} hast_table_info;
+
+typedef struct hast_stats {
+    uint64_t batches;          /* submit calls                                            */
+    uint64_t reads;            /* reads submitted                                         */
+    uint64_t bases;            /* bytes of read sequence submitted                        */
+    uint64_t lookups;          /* k-mer positions of non-N reads (two set probes = one)   */
+    uint64_t reads_with_n;     /* reads skipped by containN                               */
+    uint64_t reads_short;      /* reads shorter than k (an error in the reference)        */
+    uint64_t extra_probes;     /* bucket reads beyond the first one of a lookup           */
+    uint64_t kernel_launches;  /* launches of this library's own kernels                  */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} hast_stats;
+
+/* ---- library / context ------------------------------------------------- */
+int          hast_abi_version(void);
+int          hast_device_count(void);
+/* MultiThread ctor/dtor, classify.cpp:164-181: one worker per GPU. */
+int          hast_create(int device, hast_ctx **out);
+void         hast_destroy(hast_ctx *ctx);
+const char  *hast_last_error(const hast_ctx *ctx);      /* ctx may be NULL */
+int          hast_device(const hast_ctx *ctx);
+/* pinned host memory for batch buffers */
+int          hast_host_alloc(void **ptr, size_t bytes);
+int          hast_host_free(void *ptr);
+
+/* ---- K1: parent-unique k-mer table ------------------------------------- */
+/* load_kmers, classify.cpp:30-46 + Kmer::str2Kmer, kmer.h:153-166.
+ * begin: fix k (1..32) and the expected number of distinct keys (sizes the
+ * table at load <= 0.5); any previous table and all counts are dropped.      */
+int hast_table_begin(hast_ctx *ctx, int k, uint64_t expected_keys);
+/* add_text: `text` holds n_lines k-mers, each exactly k letters followed by
+ * '\n' (the jellyfish-dump format of build_unshared_kmers.sh:290-291, already
+ * cut at the last '\n' by the caller per classify.cpp:41).  Letters are packed
+ * with (c & 6) >> 1 (kmer.h:11), canonicalised on the device and inserted with
+ * parent tag `parent` (0 = hap0/paternal, 1 = hap1/maternal).                 */
+int hast_table_add_text(hast_ctx *ctx, const char *text, uint64_t n_lines, int parent);
+/* add_packed: the same for already packed k-mers (MSB-first, kmer.h:156-160);
+ * they need not be canonical.                                                 */
+int hast_table_add_packed(hast_ctx *ctx, const uint64_t *kmers, uint64_t n, int parent);
+/* InitAdaptor, classify.cpp:314-339: erase every canonical k-mer of `seq`
+ * from both parents' sets.  erased_out (may be NULL) receives up to cap packed
+ * canonical k-mers that were members, with their former tag in tags_out, for
+ * the "INFO : erase a adaptor kmer" log lines (classify.cpp:321-336).          */
+int hast_table_erase_seq(hast_ctx *ctx, const char *seq, uint32_t len,
+                         uint64_t *erased_out, uint8_t *tags_out, uint32_t cap,
+                         uint32_t *n_erased);
+/* g_kmers[i].size(), classify.cpp:70-71 (distinct, after erases) + layout.    */
+int hast_table_info_get(hast_ctx *ctx, hast_table_info *out);
+/* Replicate a built table on another GPU of the same process (peer copy over
+ * NVLink) instead of rebuilding it there.                                     */
+int hast_table_clone(hast_ctx *dst, hast_ctx *src);
+
+/* ---- K4 state: dense per-barcode counters ------------------------------ */
+/* BarcodeCache, classify.cpp:50-64, as int32 counts[n][2] on the device;
+ * grows preserving contents.  Barcode strings stay with the caller.          */
+int hast_reserve_barcodes(hast_ctx *ctx, uint64_t n_barcodes);
+int hast_reset_counts(hast_ctx *ctx);
+
+/* ---- K2+K3+K4 fused: one batch of reads -------------------------------- */
+/* MultiThread::submit + process_reads, classify.cpp:186-219.
+ * Read i is bases[read_off[i] .. read_off[i+1]) (ASCII, exactly the FASTQ
+ * sequence line), its barcode is the dense id barcode_id[i] < n_barcodes.
+ * Per read: any 'N' => no votes (classify.cpp:182-185,190-193); otherwise every
+ * k-mer position probes the table once and adds the tag bits to the read's
+ * two votes, which are then added to counts[barcode][0/1].
+ * Host form: asynchronous; *ticket (may be NULL) identifies the batch.        */
+int hast_submit_batch(hast_ctx *ctx, const uint8_t *bases, uint64_t n_bases,
+                      const uint32_t *read_off, const uint32_t *barcode_id,
+                      uint32_t n_reads, uint64_t *ticket);
+/* Block until the host buffers of batch `ticket` may be reused.               */
+int hast_wait_copied(hast_ctx *ctx, uint64_t ticket);
+/* Device form: the same batch with all three arrays already resident in this
+ * context's GPU memory (no copy); runs on the context's compute stream.       */
+int hast_submit_batch_device(hast_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases,
+                             const uint32_t *d_read_off, const uint32_t *d_barcode_id,
+                             uint32_t n_reads);
+int hast_sync(hast_ctx *ctx);
+
+/* ---- finish: collect the per-barcode counts ---------------------------- */
+/* MultiThread::wait + collectBarcodes + BarcodeCache::Add,
+ * classify.cpp:220-229,57-63,276-277.  Synchronises; when a communicator is
+ * attached, sums the partial counts of all ranks with ONE ncclReduce(int32,sum)
+ * to rank 0 over NVLink; copies counts[n_barcodes][2] to counts_out on rank 0
+ * (other ranks may pass NULL).  Fails with HAST_E_SHORT_READ if any read was
+ * shorter than k.                                                             */
+int hast_finish(hast_ctx *ctx, int32_t *counts_out, uint64_t n_barcodes);
+int hast_stats_get(hast_ctx *ctx, hast_stats *out);
+/* raw device pointer of the int32 counts[n][2] array (for zero-copy views)    */
+int hast_counts_device_ptr(hast_ctx *ctx, void **ptr, uint64_t *n_barcodes);
+/* CUDA event timing of the work submitted between the two marks (ms), on the
+ * context's compute stream.                                                   */
+int hast_timer_start(hast_ctx *ctx);
+int hast_timer_stop(hast_ctx *ctx, float *ms);
+
+/* ---- multi-GPU ---------------------------------------------------------- */
+/* single process, one context per GPU (bin/classify): ncclCommInitAll         */
+int hast_comm_init_all(hast_ctx **ctxs, int n);
+/* one process per GPU (torchrun): 128-byte ncclUniqueId made on rank 0 and
+ * distributed by the caller                                                   */
+int hast_comm_unique_id(void *id128);
+int hast_comm_init_rank(hast_ctx *ctx, int nranks, int rank, const void *id128);
+
+/* ---- standalone K2 / K3 (parity tests, ncu evidence) ------------------- */
+/* Kmer::chopRead2Kmer, kmer.h:169-194: canonical k-mers of every read, written
+ * to kmers_out[kmer_off[i] + j] with kmer_off[i] = read_off[i] - i*(k-1)
+ * (reads shorter than k or containing 'N' are still extracted when long
+ * enough; has_n_out[i] = containN).  Host buffers.                            */
+int hast_extract_kmers(hast_ctx *ctx, const uint8_t *bases, uint64_t n_bases,
+                       const uint32_t *read_off, uint32_t n_reads,
+                       uint64_t *kmers_out, uint64_t n_kmers_out, uint8_t *has_n_out);
+/* g_kmers[0/1].find, classify.cpp:195-202: tag bits (bit0 hap0, bit1 hap1) of
+ * n canonical packed k-mers.  Host buffers.                                   */
+int hast_lookup(hast_ctx *ctx, const uint64_t *canonical, uint64_t n, uint8_t *tags_out);
+/* Device-resident forms used by bench.py / ncu: time only the kernel.         */
+int hast_extract_kmers_device(hast_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases,
+                              const uint32_t *d_read_off, uint32_t n_reads,
+                              uint64_t *d_kmers_out, uint8_t *d_has_n_out);
+int hast_lookup_device(hast_ctx *ctx, const uint64_t *d_canonical, uint64_t n, uint8_t *d_tags_out);
+/* Random 32-byte-sector gather over the table's own memory: the measured
+ * random-access roofline the lookup kernel is compared with.  Returns the
+ * achieved GB/s of n_probes independent sector reads.                         */
+int hast_gather_roofline(hast_ctx *ctx, uint64_t n_probes, uint64_t span_bytes, float *gbps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

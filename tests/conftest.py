@@ -1,0 +1,49 @@
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _have_gpu() -> bool:
+    try:
+        from hast_b200 import capi
+        return capi.load_library().hast_device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build what is missing (cheap no-op when the tree is already built)."""
+    need = [ROOT / "hast_b200/lib/libhast_b200.so", ROOT / "hast_b200/lib/libhast_tools.so",
+            ROOT / "bin/classify", ROOT / "bin/mergeResult", ROOT / "oracle/liboracle.so"]
+    if not all(p.exists() for p in need):
+        subprocess.run(["make", "-C", str(ROOT), "all"], check=True, capture_output=True)
+    yield
+
+
+@pytest.fixture(scope="session")
+def engine():
+    from hast_b200.capi import Engine
+    e = Engine(0)
+    yield e
+    e.close()
