@@ -64,6 +64,15 @@ __device__ __forceinline__ void set_bits(uint32_t* bits, uint32_t from, uint32_t
         from += n;
     }
 }
+__device__ __forceinline__ void clear_bits(uint32_t* bits, uint32_t from, uint32_t to) {   // [from, to)
+    while (from < to) {
+        const uint32_t w = from >> 5, lo = from & 31u;
+        const uint32_t n = min(32u - lo, to - from);
+        const uint32_t m = (n == 32u ? 0xFFFFFFFFu : ((1u << n) - 1u)) << lo;
+        atomicAnd(&bits[w], ~m);
+        from += n;
+    }
+}
 __device__ __forceinline__ bool any_bits(const uint32_t* bits, uint32_t from, uint32_t to) {
     while (from < to) {
         const uint32_t w = from >> 5, lo = from & 31u;
@@ -172,6 +181,8 @@ tile_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_b
                 const bool too_short = L < (uint32_t)k;
                 if (MODE == MODE_EXTRACT) {
                     if (has_n_out) has_n_out[r0 + r] = has_n ? 1 : 0;
+                    // chopRead2Kmer itself packs an 'N' like any byte (kmer.h:11): drop the N marks
+                    if (has_n) clear_bits(s_bad, s, e);
                     if (too_short) set_bits(s_bad, s, e);
                     else set_bits(s_bad, e - (uint32_t)k + 1u, e);
                 } else {

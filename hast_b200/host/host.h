@@ -1,0 +1,112 @@
+// host.h -- host side of bin/classify: the reference's process interface
+// (01.classify_stlfr_reads/classify.cpp) rebuilt as a streaming pipeline
+//     reader (read/inflate) -> parser threads -> pinned batches -> GPU contexts
+// on top of the C ABI in include/hast_b200.h.  Nothing here computes k-mers or
+// looks anything up: that happens only on the device.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace hasthost {
+
+// ---- command line (classify.cpp:375-428) -----------------------------------
+struct Options {
+    std::string hap0, hap1;
+    std::vector<std::string> reads;
+    int threads = 8;                       // -t: here the number of FASTQ parser threads
+    double weight0 = 1.0, weight1 = 1.0;   // classify.cpp:22-23
+    std::string adaptor_f = "CTGTCTCTTATACACATCTTAGGAAGACAAGCACTGACGACATGA";   // classify.cpp:312
+    std::string adaptor_r = "TCTGCTGAGTCGAGAACGTCTCTGTGAGCCAAGGAGTTGCTCTGG";   // classify.cpp:313
+    // extensions (long options only; the reference rejects them, so no clash)
+    int gpus = 0;                          // 0 = all visible
+    std::string stats_json;                // throughput side output
+    size_t batch_bytes = 32u << 20;        // raw FASTQ text per parse block
+};
+// returns 0 to run, otherwise the process exit code (255 after printing usage)
+int parse_options(int argc, char** argv, Options& opt);
+void print_usage();
+
+// ---- k-mer list files (classify.cpp:30-46) ----------------------------------
+struct KmerList {
+    std::string text;        // n_lines lines of k letters + '\n', ready for hast_table_add_text
+    uint64_t n_lines = 0;    // "total_kmer" of classify.cpp:45
+    int k = 0;
+};
+// index 0 derives k from the first line; index 1 takes k from the caller.
+// Returns "" or an error message.
+std::string load_kmer_list(const std::string& path, int index, int k_in, KmerList& out);
+
+// ---- barcode interning ------------------------------------------------------
+// Barcodes are arbitrary byte strings (tools/mark_library.sh:24 makes lib2_a_b_c);
+// every distinct one seen gets a dense global id, whether or not it ever scores
+// (classify.cpp:191,208 create the map entry through key -1).
+class BarcodeIndex {
+public:
+    BarcodeIndex();
+    ~BarcodeIndex();
+    uint32_t intern(const char* s, size_t n);
+    uint32_t size() const { return next_id_.load(std::memory_order_acquire); }
+    // names in id order (call after all parsing finished)
+    void export_names(std::vector<std::string>& out) const;
+private:
+    struct Shard;
+    static constexpr int kShards = 256;
+    std::unique_ptr<Shard[]> shards_;
+    std::atomic<uint32_t> next_id_{0};
+};
+
+// ---- FASTQ blocks -------------------------------------------------------------
+// A block holds whole records only (the reader cuts at a newline where the line
+// count is a multiple of four, classify.cpp:257-269 framing).
+struct TextBlock {
+    std::vector<char> data;
+    size_t len = 0;
+    bool last_of_file = false;   // the final block may end in a partial record / unterminated line
+};
+
+// One parsed batch in pinned memory, laid out for hast_submit_batch.
+struct Batch {
+    uint8_t* bases = nullptr;   size_t cap_bases = 0;  uint64_t n_bases = 0;
+    uint32_t* read_off = nullptr; uint32_t* barcode_id = nullptr; size_t cap_reads = 0;
+    uint32_t n_reads = 0;
+    uint32_t max_barcode = 0;
+    std::string error;
+};
+
+// classify.cpp:112-119
+inline void parse_name(const char* head, size_t len, size_t& start, size_t& blen) {
+    long s = -1, e = -1;
+    for (size_t i = 0; i < len; ++i) {
+        if (head[i] == '#') s = (long)i;
+        if (head[i] == '/') e = (long)i;
+    }
+    long cnt = e - s - 1;
+    start = (size_t)(s + 1);
+    blen = (cnt < 0 || (size_t)(s + 1 + cnt) > len) ? len - (size_t)(s + 1) : (size_t)cnt;
+}
+
+// Parse one block into a batch.  Returns false on a framing error that the
+// reference would have died on (message in batch.error).
+bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out);
+
+// ---- haplotype call + table output (classify.cpp:66-102) ----------------------
+int get_hap(const std::string& barcode, int c0, int c1, uint64_t n0, uint64_t n1, double w0, double w1);
+void print_table(FILE* out, const std::vector<std::string>& names, const int32_t* counts, uint64_t n0,
+                 uint64_t n1, double w0, double w1);
+
+// ---- the pipeline ---------------------------------------------------------------
+struct RunStats {
+    uint64_t reads = 0, bases = 0, barcodes = 0, lookups = 0, text_bytes = 0;
+    double t_table = 0, t_reads = 0, t_finish = 0, t_print = 0, t_total = 0;
+    int gpus = 0, parser_threads = 0;
+    uint64_t table_bytes = 0, size0 = 0, size1 = 0, kernel_launches = 0;
+};
+int run_classify(const Options& opt, RunStats& st);
+
+}  // namespace hasthost
