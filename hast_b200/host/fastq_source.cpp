@@ -1,0 +1,109 @@
+// fastq_source.cpp -- see fastq_source.h
+#include "fastq_source.h"
+
+#include <emmintrin.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <cstring>
+
+namespace hasthost {
+
+size_t count_newlines(const char* p, size_t n) {
+    size_t c = 0, i = 0;
+    const __m128i nl = _mm_set1_epi8('\n');
+    for (; i + 16 <= n; i += 16) {
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p + i));
+        c += (size_t)__builtin_popcount((unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, nl)));
+    }
+    for (; i < n; ++i) c += p[i] == '\n';
+    return c;
+}
+
+FastqSource::~FastqSource() {
+    if (gz_) gzclose(gz_);
+    if (fd_ >= 0) close(fd_);
+}
+
+std::string FastqSource::open(const std::string& path) {
+    path_ = path;
+    const size_t n = path.size();
+    const bool gz = n > 3 && path[n - 3] == '.' && path[n - 2] == 'g' && path[n - 1] == 'z';   // classify.cpp:245-250
+    if (gz) {
+        gz_ = gzopen(path.c_str(), "rb");
+        if (!gz_) return "cannot open " + path;
+        gzbuffer(gz_, 1u << 20);
+    } else {
+        fd_ = ::open(path.c_str(), O_RDONLY);
+        if (fd_ < 0) return "cannot open " + path + ": " + strerror(errno);
+#ifdef POSIX_FADV_SEQUENTIAL
+        posix_fadvise(fd_, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+    }
+    return "";
+}
+
+size_t FastqSource::raw_read(char* dst, size_t n, std::string& err) {
+    if (gz_) {
+        const unsigned want = (unsigned)std::min<size_t>(n, 1u << 30);
+        const int r = gzread(gz_, dst, want);
+        if (r < 0) {
+            int e = 0;
+            err = std::string("gzread failed on ") + path_ + ": " + gzerror(gz_, &e);
+            return 0;
+        }
+        return (size_t)r;
+    }
+    for (;;) {
+        const ssize_t r = ::read(fd_, dst, n);
+        if (r >= 0) return (size_t)r;
+        if (errno == EINTR) continue;
+        err = "read failed on " + path_ + ": " + strerror(errno);
+        return 0;
+    }
+}
+
+bool FastqSource::next(TextBlock& blk, size_t target, std::string& err) {
+    if (eof_ && carry_.empty()) return false;
+    size_t cap = std::max(blk.data.size(), target + carry_.size() + 4096);
+    blk.data.resize(cap);
+    size_t len = carry_.size();
+    if (len) memcpy(blk.data.data(), carry_.data(), len);
+    uint64_t lines = carry_lines_;
+    carry_.clear();
+    carry_lines_ = 0;
+    blk.last_of_file = false;
+    for (;;) {
+        while (!eof_ && len < target) {
+            const size_t n = raw_read(blk.data.data() + len, cap - len, err);
+            if (!err.empty()) return false;
+            if (n == 0) { eof_ = true; break; }
+            lines += count_newlines(blk.data.data() + len, n);
+            len += n;
+        }
+        if (eof_) {                                   // whatever is left, partial record included
+            blk.len = len;
+            blk.last_of_file = true;
+            bytes_out_ += len;
+            return len > 0;
+        }
+        if (lines >= 4) break;
+        target *= 2;                                  // a record longer than the block: keep reading
+        cap = target + 4096;
+        blk.data.resize(cap);
+    }
+    // cut after the last newline that closes a whole record
+    const char* d = blk.data.data();
+    const uint32_t leftover = (uint32_t)(lines & 3u);
+    const char* q = (const char*)memrchr(d, '\n', len);
+    for (uint32_t i = 0; i < leftover; ++i) q = (const char*)memrchr(d, '\n', (size_t)(q - d));
+    const size_t cut = (size_t)(q - d) + 1;
+    carry_.assign(d + cut, d + len);
+    carry_lines_ = leftover;
+    blk.len = cut;
+    bytes_out_ += cut;
+    return true;
+}
+
+}  // namespace hasthost

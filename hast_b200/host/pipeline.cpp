@@ -1,0 +1,380 @@
+// pipeline.cpp -- the streaming host pipeline of bin/classify.
+//
+//   reader thread   : every --read file in turn, read()/gzread() into text blocks of
+//                     whole records                       (processFastq, classify.cpp:238-269)
+//   parser threads  : block -> pinned batch; barcodes interned to dense ids
+//                     (parseName :112-119; MultiThread::submit's Buffer :121-127,211-219)
+//   one thread/GPU  : hast_submit_batch (async H2D + fused kernel), batches taken from a
+//                     shared queue, i.e. read batches are sharded over the GPUs
+//                     (the reference round-robins buffers over worker threads, :214-218)
+//   finish          : hast_finish on every GPU at once -> one ncclReduce -> counts on GPU 0
+//                     (wait / collectBarcodes / Add, :220-229,57-63)
+//
+// The k-mer table is built once on GPU 0 and cloned to the others over NVLink.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#include "../../include/hast_b200.h"
+#include "fastq_source.h"
+#include "host.h"
+
+namespace hasthost {
+
+namespace {
+
+double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <class T>
+class Queue {
+public:
+    explicit Queue(size_t cap) : cap_(cap) {}
+    bool push(T v) {
+        std::unique_lock<std::mutex> lk(mu_);
+        not_full_.wait(lk, [&] { return q_.size() < cap_ || closed_; });
+        if (closed_) return false;
+        q_.push_back(std::move(v));
+        not_empty_.notify_one();
+        return true;
+    }
+    bool pop(T& v) {
+        std::unique_lock<std::mutex> lk(mu_);
+        not_empty_.wait(lk, [&] { return !q_.empty() || done_ || closed_; });
+        if (closed_ || q_.empty()) return false;
+        v = std::move(q_.front());
+        q_.pop_front();
+        not_full_.notify_one();
+        return true;
+    }
+    void finish() {                  // producers are done: consumers drain then stop
+        std::lock_guard<std::mutex> lk(mu_);
+        done_ = true;
+        not_empty_.notify_all();
+    }
+    void abort() {                   // error: everybody stops now
+        std::lock_guard<std::mutex> lk(mu_);
+        closed_ = true;
+        not_empty_.notify_all();
+        not_full_.notify_all();
+    }
+private:
+    std::mutex mu_;
+    std::condition_variable not_full_, not_empty_;
+    std::deque<T> q_;
+    size_t cap_;
+    bool done_ = false, closed_ = false;
+};
+
+struct Shared {
+    std::mutex mu;
+    std::string error;
+    std::atomic<bool> failed{false};
+    void fail(const std::string& e) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (error.empty()) error = e;
+        failed = true;
+    }
+};
+
+void logtime() {                     // classify.cpp:17-21
+    time_t t = time(nullptr);
+    fprintf(stderr, "%s\n", ctime(&t));
+}
+
+std::string kmer_to_string(uint64_t w, int k) {     // Kmer::ToBaseStr + BaseStr2Str, kmer.h:244-254,14-25
+    std::string s((size_t)k, 'A');
+    for (int i = 0; i < k; ++i) { s[(size_t)(k - 1 - i)] = "ACTG"[w & 3]; w >>= 2; }
+    return s;
+}
+
+}  // namespace
+
+int run_classify(const Options& opt, RunStats& st) {
+    const double t_start = now();
+    // HAST_PARSE_ONLY=1: host front end only (reader, framing, parseName, interning, ordering);
+    // prints barcode \t reads \t bases.  A diagnostic for the host logic, it classifies nothing.
+    const bool parse_only = getenv("HAST_PARSE_ONLY") != nullptr;
+    int n_dev = parse_only ? 1 : hast_device_count();
+    if (n_dev <= 0) {
+        fprintf(stderr, "ERROR : no CUDA device found; this build of classify has no CPU path\n");
+        return 1;
+    }
+    int n_gpu = parse_only ? 1 : (opt.gpus > 0 ? std::min(opt.gpus, n_dev) : n_dev);
+    st.gpus = n_gpu;
+    st.parser_threads = opt.threads;
+
+    std::vector<hast_ctx*> ctx((size_t)n_gpu, nullptr);
+    auto cleanup = [&] { for (hast_ctx* c : ctx) hast_destroy(c); };
+    for (int g = 0; g < n_gpu && !parse_only; ++g) {
+        if (hast_create(g, &ctx[(size_t)g]) != HAST_OK) {
+            fprintf(stderr, "ERROR : %s\n", hast_last_error(nullptr));
+            cleanup();
+            return 1;
+        }
+    }
+#define HCHECK(c, call)                                                     \
+    do {                                                                    \
+        if ((call) != HAST_OK) {                                            \
+            fprintf(stderr, "ERROR : %s\n", hast_last_error(c));            \
+            cleanup();                                                      \
+            return 1;                                                       \
+        }                                                                   \
+    } while (0)
+
+    fprintf(stderr, "__START__\n use hap0 weight %g\n use hap1 weight %g\n", opt.weight0, opt.weight1);
+    fprintf(stderr, " use %d GPU(s), %d parser thread(s)\n", n_gpu, opt.threads);
+    logtime();
+
+    // ---- k-mer table (load_kmers x2 + InitAdaptor, classify.cpp:433-437) -----------
+    if (!parse_only) {
+        KmerList l0, l1;
+        fprintf(stderr, "__load hap0 kmers__\n");
+        std::string e = load_kmer_list(opt.hap0, 0, 0, l0);
+        if (!e.empty()) { fprintf(stderr, "ERROR : %s\n", e.c_str()); cleanup(); return 1; }
+        fprintf(stderr, "Recorded %llu haplotype 0 specific %d-mers\n", (unsigned long long)l0.n_lines, l0.k);
+        fprintf(stderr, "__load hap1 kmers__\n");
+        e = load_kmer_list(opt.hap1, 1, l0.k, l1);
+        if (!e.empty()) { fprintf(stderr, "ERROR : %s\n", e.c_str()); cleanup(); return 1; }
+        fprintf(stderr, "Recorded %llu haplotype 1 specific %d-mers\n", (unsigned long long)l1.n_lines, l0.k);
+
+        uint64_t expected = l0.n_lines + l1.n_lines;
+        for (int attempt = 0;; ++attempt) {
+            HCHECK(ctx[0], hast_table_begin(ctx[0], l0.k, expected));
+            int rc = hast_table_add_text(ctx[0], l0.text.data(), l0.n_lines, 0);
+            if (rc == HAST_OK) rc = hast_table_add_text(ctx[0], l1.text.data(), l1.n_lines, 1);
+            if (rc == HAST_E_TABLE_FULL && attempt < 4) { expected = expected * 2 + 64; continue; }
+            if (rc != HAST_OK) { fprintf(stderr, "ERROR : %s\n", hast_last_error(ctx[0])); cleanup(); return 1; }
+            break;
+        }
+        fprintf(stderr, "Adaptor forward :%s\nAdaptor reverse :%s\n", opt.adaptor_f.c_str(), opt.adaptor_r.c_str());
+        for (const std::string* ad : {&opt.adaptor_f, &opt.adaptor_r}) {
+            std::vector<uint64_t> er(ad->size() + 1);
+            std::vector<uint8_t> tg(ad->size() + 1);
+            uint32_t n = 0;
+            HCHECK(ctx[0], hast_table_erase_seq(ctx[0], ad->data(), (uint32_t)ad->size(), er.data(), tg.data(),
+                                                (uint32_t)er.size(), &n));
+            for (uint32_t i = 0; i < n && i < er.size(); ++i)       // classify.cpp:319-337
+                for (int h = 0; h < 2; ++h)
+                    if (tg[i] & (1 << h))
+                        fprintf(stderr, " INFO : erase a adaptor kmer from hap %d ; kmer= %s\n", h,
+                                kmer_to_string(er[i], l0.k).c_str());
+        }
+        hast_table_info ti;
+        HCHECK(ctx[0], hast_table_info_get(ctx[0], &ti));
+        st.size0 = ti.size[0];
+        st.size1 = ti.size[1];
+        st.table_bytes = ti.bytes;
+        fprintf(stderr, " table : %llu buckets (%.1f MiB), %llu distinct k-mers, %llu displaced, |S0|=%llu |S1|=%llu\n",
+                (unsigned long long)ti.n_buckets, ti.bytes / 1048576.0, (unsigned long long)ti.n_entries,
+                (unsigned long long)ti.n_displaced, (unsigned long long)ti.size[0], (unsigned long long)ti.size[1]);
+        for (int g = 1; g < n_gpu; ++g) HCHECK(ctx[(size_t)g], hast_table_clone(ctx[(size_t)g], ctx[0]));
+    }
+    if (n_gpu > 1 && !parse_only) HCHECK(ctx[0], hast_comm_init_all(ctx.data(), n_gpu));
+    st.t_table = now() - t_start;
+    logtime();
+
+    // ---- streaming classification ---------------------------------------------------
+    const double t_reads0 = now();
+    const size_t block_bytes = std::max<size_t>(opt.batch_bytes, 1u << 16);
+    const size_t n_batches = (size_t)opt.threads + 3 * (size_t)n_gpu + 1;
+    Shared sh;
+    BarcodeIndex index;
+    Queue<TextBlock*> q_text((size_t)opt.threads + 2), q_text_free(1u << 20);
+    Queue<Batch*> q_batch(n_batches), q_batch_free(1u << 20);
+    std::vector<TextBlock> text_pool((size_t)opt.threads + 3);
+    std::vector<Batch> batch_pool(n_batches);
+    for (auto& t : text_pool) q_text_free.push(&t);
+    bool alloc_ok = true;
+    for (auto& b : batch_pool) {
+        b.cap_bases = block_bytes + 4096;
+        b.cap_reads = block_bytes / 24 + 16;
+        void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+        if (parse_only) {
+            p0 = malloc(b.cap_bases); p1 = malloc((b.cap_reads + 1) * 4); p2 = malloc(b.cap_reads * 4);
+        } else if (hast_host_alloc(&p0, b.cap_bases) || hast_host_alloc(&p1, (b.cap_reads + 1) * 4) ||
+                   hast_host_alloc(&p2, b.cap_reads * 4)) {
+            alloc_ok = false;
+            break;
+        }
+        b.bases = (uint8_t*)p0; b.read_off = (uint32_t*)p1; b.barcode_id = (uint32_t*)p2;
+        q_batch_free.push(&b);
+    }
+    auto free_batches = [&] {
+        for (auto& b : batch_pool) {
+            if (parse_only) { free(b.bases); free(b.read_off); free(b.barcode_id); }
+            else { hast_host_free(b.bases); hast_host_free(b.read_off); hast_host_free(b.barcode_id); }
+        }
+    };
+    if (!alloc_ok) {
+        fprintf(stderr, "ERROR : pinned host allocation failed: %s\n", hast_last_error(nullptr));
+        free_batches(); cleanup();
+        return 1;
+    }
+    auto abort_all = [&] { q_text.abort(); q_text_free.abort(); q_batch.abort(); q_batch_free.abort(); };
+
+    std::atomic<uint64_t> text_bytes{0};
+    std::thread reader([&] {
+        for (const std::string& path : opt.reads) {
+            fprintf(stderr, "__process read: %s\n", path.c_str());
+            FastqSource src;
+            std::string e = src.open(path);
+            if (!e.empty()) { sh.fail(e); abort_all(); return; }
+            for (;;) {
+                TextBlock* blk = nullptr;
+                if (!q_text_free.pop(blk)) return;
+                std::string err;
+                const bool more = src.next(*blk, block_bytes - 8192, err);
+                if (!err.empty()) { sh.fail(err); abort_all(); return; }
+                if (!more) { q_text_free.push(blk); break; }
+                if (!q_text.push(blk)) return;
+            }
+            text_bytes += src.bytes_out();
+        }
+        q_text.finish();
+    });
+
+    std::atomic<int> parsers_left{opt.threads};
+    std::vector<std::thread> parsers;
+    for (int t = 0; t < opt.threads; ++t)
+        parsers.emplace_back([&] {
+            TextBlock* blk = nullptr;
+            while (q_text.pop(blk)) {
+                Batch* b = nullptr;
+                if (!q_batch_free.pop(b)) break;
+                if (blk->len + 4096 > b->cap_bases) {          // an oversized block (very long records)
+                    sh.fail("FASTQ record larger than the batch buffer; raise HAST_BLOCK_MB");
+                    abort_all();
+                    break;
+                }
+                const bool ok = parse_block(*blk, index, *b);
+                q_text_free.push(blk);
+                if (!ok) { sh.fail(b->error); abort_all(); break; }
+                if (!q_batch.push(b)) break;
+            }
+            if (--parsers_left == 0) q_batch.finish();
+        });
+
+    std::atomic<uint64_t> n_reads{0}, n_bases{0};
+    std::vector<uint64_t> po_tally;                      // parse-only: reads, bases per barcode id
+    std::vector<std::thread> gpu_threads;
+    for (int g = 0; g < n_gpu; ++g)
+        gpu_threads.emplace_back([&, g] {
+            hast_ctx* c = ctx[(size_t)g];
+            uint64_t reserved = 0;
+            std::deque<std::pair<uint64_t, Batch*>> inflight;
+            Batch* b = nullptr;
+            while (parse_only && q_batch.pop(b)) {
+                for (uint32_t i = 0; i < b->n_reads; ++i) {
+                    const uint32_t id = b->barcode_id[i];
+                    if (po_tally.size() < 2 * ((size_t)id + 1)) po_tally.resize(2 * ((size_t)id + 1), 0);
+                    po_tally[2 * (size_t)id] += 1;
+                    po_tally[2 * (size_t)id + 1] += b->read_off[i + 1] - b->read_off[i];
+                }
+                n_reads += b->n_reads;
+                n_bases += b->n_bases;
+                q_batch_free.push(b);
+            }
+            if (parse_only) return;
+            while (q_batch.pop(b)) {
+                const uint64_t need = (uint64_t)b->max_barcode + 1;
+                if (need > reserved) {
+                    reserved = std::max<uint64_t>(need, index.size());
+                    if (hast_reserve_barcodes(c, reserved) != HAST_OK) { sh.fail(hast_last_error(c)); abort_all(); break; }
+                }
+                uint64_t ticket = 0;
+                if (hast_submit_batch(c, b->bases, b->n_bases, b->read_off, b->barcode_id, b->n_reads, &ticket) != HAST_OK) {
+                    sh.fail(hast_last_error(c)); abort_all(); break;
+                }
+                n_reads += b->n_reads;
+                n_bases += b->n_bases;
+                inflight.emplace_back(ticket, b);
+                while (inflight.size() > 2) {                  // double buffering: two batches in flight per GPU
+                    hast_wait_copied(c, inflight.front().first);
+                    q_batch_free.push(inflight.front().second);
+                    inflight.pop_front();
+                }
+            }
+            hast_sync(c);
+            for (auto& f : inflight) q_batch_free.push(f.second);
+        });
+
+    reader.join();
+    for (auto& t : parsers) t.join();
+    for (auto& t : gpu_threads) t.join();
+    if (sh.failed) {
+        fprintf(stderr, "ERROR : %s\n", sh.error.c_str());
+        free_batches(); cleanup();
+        return 1;
+    }
+    st.reads = n_reads;
+    st.bases = n_bases;
+    st.text_bytes = text_bytes;
+    st.t_reads = now() - t_reads0;
+    logtime();
+    fprintf(stderr, "__process read done__\n");
+
+    if (parse_only) {
+        std::vector<std::string> names;
+        index.export_names(names);
+        po_tally.resize(2 * names.size(), 0);
+        std::vector<uint32_t> order(names.size());
+        for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return names[a] < names[b]; });
+        for (uint32_t id : order)
+            printf("%s\t%llu\t%llu\n", names[id].c_str(), (unsigned long long)po_tally[2 * (size_t)id],
+                   (unsigned long long)po_tally[2 * (size_t)id + 1]);
+        free_batches();
+        st.t_total = now() - t_start;
+        return 0;
+    }
+
+    // ---- collect (collectBarcodes / Add, classify.cpp:226-229,57-63) -------------------
+    const double t_fin0 = now();
+    const uint64_t n_bc = index.size();
+    st.barcodes = n_bc;
+    std::vector<int32_t> counts(std::max<uint64_t>(n_bc, 1) * 2, 0);
+    {
+        std::vector<int> rcs((size_t)n_gpu, 0);
+        std::vector<std::thread> fin;
+        for (int g = 0; g < n_gpu; ++g)
+            fin.emplace_back([&, g] {
+                hast_ctx* c = ctx[(size_t)g];
+                int rc = hast_reserve_barcodes(c, n_bc);
+                if (rc == HAST_OK) rc = hast_finish(c, g == 0 ? counts.data() : nullptr, n_bc);
+                rcs[(size_t)g] = rc;
+            });
+        for (auto& t : fin) t.join();
+        for (int g = 0; g < n_gpu; ++g)
+            if (rcs[(size_t)g] != HAST_OK) {
+                fprintf(stderr, "ERROR : %s\n", hast_last_error(ctx[(size_t)g]));
+                free_batches(); cleanup();
+                return 1;
+            }
+    }
+    for (int g = 0; g < n_gpu; ++g) {
+        hast_stats hs;
+        if (hast_stats_get(ctx[(size_t)g], &hs) == HAST_OK) { st.lookups += hs.lookups; st.kernel_launches += hs.kernel_launches; }
+    }
+    st.t_finish = now() - t_fin0;
+
+    // ---- output (printBarcodeInfos, classify.cpp:447) ---------------------------------
+    fprintf(stderr, "__print result__\n");
+    const double t_pr0 = now();
+    std::vector<std::string> names;
+    index.export_names(names);
+    print_table(stdout, names, counts.data(), st.size0, st.size1, opt.weight0, opt.weight1);
+    st.t_print = now() - t_pr0;
+    logtime();
+    fprintf(stderr, "__END__\n");
+    free_batches();
+    cleanup();
+    st.t_total = now() - t_start;
+    return 0;
+}
+
+}  // namespace hasthost

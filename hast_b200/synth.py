@@ -41,6 +41,7 @@ class TrioSpec:
     decoy_kmers: int = 0          # extra random k-mers per parent list (inflates the table)
     lowercase_frac: float = 0.0   # reads written in lowercase (kmer.h:11 is case-insensitive)
     seed: int = 1
+    read_seed: int = 51           # reads only: ranks of a multi-GPU run draw different reads of one trio
 
 
 @dataclass
@@ -259,7 +260,7 @@ def make_trio(spec: TrioSpec, device: str = "cpu", keep_reads_on_device: bool = 
     fstart = (g.random((B, 3)) * (G - flen)).astype(np.int64)
 
     # 4. read pairs
-    g = rng(51)
+    g = rng(spec.read_seed)
     P = spec.n_pairs
     if spec.zipf_alpha:
         w = 1.0 / np.power(np.arange(1, B + 1, dtype=np.float64), spec.zipf_alpha)

@@ -567,10 +567,26 @@ int ho_merge_result(const char *const *inputs, int n_inputs, float w0, float w1,
             char *nl = (char *)memchr(buf + pos, '\n', n - pos);
             if (!nl) break;                                    /* :124 loop ends at eof */
             *nl = 0;
+            /* mergeResult.cpp:21-30 AddLine: is>>barcode>>type>>hap0>>hap1.  operator>> skips
+             * leading whitespace, so a line whose barcode is the empty string ("\t-1\t0\t0", which
+             * classify prints for headers like "@r#/1") is read shifted by one column: barcode "-1",
+             * type 0, hap0 0, and hap1 fails -> 0 (C++11 writes 0 on a failed extraction). */
             char bc[4096];
-            int type, h0, h1;
-            /* mergeResult.cpp:21-30 AddLine: is>>barcode>>type>>hap0>>hap1 */
-            if (sscanf(buf + pos, "%4095s %d %d %d", bc, &type, &h0, &h1) != 4) { free(buf); return -2; }
+            int v[3] = { 0, 0, 0 };
+            const char *q = buf + pos;
+            size_t bl = 0;
+            while (*q == ' ' || *q == '\t') q++;
+            while (*q && *q != ' ' && *q != '\t' && bl < sizeof bc - 1) bc[bl++] = *q++;
+            bc[bl] = 0;
+            for (int i = 0; i < 3; i++) {
+                char *e;
+                while (*q == ' ' || *q == '\t') q++;
+                long x = strtol(q, &e, 10);
+                if (e == q) break;                              /* failed extraction: this and later stay 0 */
+                v[i] = (int)x;
+                q = e;
+            }
+            int h0 = v[1], h1 = v[2];
             if (intended) {
                 ho_incr(&m, bc, strlen(bc), 0, h0);
                 ho_incr(&m, bc, strlen(bc), 1, h1);

@@ -1,0 +1,125 @@
+"""CPU: host-side logic of bin/classify and bin/mergeResult (no GPU needed).
+
+CLI contract (classify.cpp:375-428), FASTQ framing / gzip / parseName / barcode
+interning / output order through the HAST_PARSE_ONLY diagnostic, and mergeResult
+against the golden produced by the reference binary.
+"""
+import json
+import os
+import subprocess
+from collections import Counter
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cases
+import oracle as orc
+
+ROOT = Path(__file__).resolve().parent.parent
+CLASSIFY = ROOT / "bin" / "classify"
+MERGE = ROOT / "bin" / "mergeResult"
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def run(cmd, **kw):
+    return subprocess.run([str(c) for c in cmd], capture_output=True, **kw)
+
+
+@pytest.mark.parametrize("args", [[], ["-h"], ["--help"], ["-l", "x"], ["--bogus"], ["--hap0", "a", "--hap1", "b"],
+                                  ["--hap0", "a", "--read", "r"], ["--hap0", "a", "--hap1", "b", "--read", "r", "-t", "0"]])
+def test_usage_and_exit_255(args):
+    r = run([CLASSIFY] + args)
+    assert r.returncode == 255                      # `return -1` from main, classify.cpp:421-427
+    assert b"Uasge" in r.stderr and r.stdout == b""  # usage goes to stderr, stdout stays pure
+    ref = orc.ref_binary("classify")
+    if ref is not None:
+        assert run([ref] + args).returncode == 255
+
+
+def parse_only(files, threads=3, block_mb=None):
+    env = dict(os.environ, HAST_PARSE_ONLY="1")
+    if block_mb is not None:
+        env["HAST_BLOCK_MB"] = str(block_mb)
+    cmd = [CLASSIFY, "--hap0", "x", "--hap1", "y", "-t", str(threads)]
+    for f in files:
+        cmd += ["--read", f]
+    r = run(cmd, env=env)
+    assert r.returncode == 0, r.stderr[-400:]
+    return r.stdout
+
+
+def expected_parse(heads, reads):
+    n, b = Counter(), Counter()
+    for h, r in zip(heads, reads):
+        bc = orc.parse_name(h)
+        n[bc] += 1
+        b[bc] += len(r)
+    return b"".join(b"%s\t%d\t%d\n" % (k, n[k], b[k]) for k in sorted(n))
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_front_end_framing_barcodes_and_order(tmp_path, crlf):
+    c = cases.adversarial_case(21, 3000, seed=77)
+    heads = c["heads"] + [b"@weird header no separators", b"@x/1#tail_bc", b"@a#b#c/d/e"]
+    reads = c["reads"] + [b"ACGT" * 10, b"TTTT" * 12, b"GG" * 30]
+    cases.write_fastq(tmp_path / "a.fq", heads[:1000], reads[:1000], crlf=crlf)
+    cases.write_fastq(tmp_path / "b.fq.gz", heads[1000:], reads[1000:], crlf=crlf, trailing_newline=False)
+    got = parse_only([tmp_path / "a.fq", tmp_path / "b.fq.gz"])
+    if crlf:                                         # '\r' stays part of header and sequence
+        heads = [h + b"\r" for h in heads]
+        reads = [r + b"\r" for r in reads]
+    assert got == expected_parse(heads, reads)
+    # tiny blocks: many block boundaries, same answer; file listed twice counts twice
+    assert parse_only([tmp_path / "a.fq", tmp_path / "b.fq.gz"], threads=2, block_mb=0) == got
+    twice = parse_only([tmp_path / "a.fq", tmp_path / "a.fq"])
+    assert twice == expected_parse(heads[:1000] * 2, reads[:1000] * 2)
+
+
+def test_front_end_eof_semantics(tmp_path):
+    # classify.cpp:257-269: a terminated header is processed with whatever follows; an unterminated one is dropped
+    rec = b"@r1#1_1_1/1\nACGTACGTACGTACGTACGTACGT\n+\nFFFFFFFFFFFFFFFFFFFFFFFF\n"
+    (tmp_path / "a.fq").write_bytes(rec + b"@r2#2_2_2/1\nACGTACGTACGTACGTACGTAAAA")          # seq unterminated, no + / qual
+    assert parse_only([tmp_path / "a.fq"]) == b"1_1_1\t1\t24\n2_2_2\t1\t24\n"
+    (tmp_path / "b.fq").write_bytes(rec + b"@r2#2_2_2/1")                                       # unterminated header
+    assert parse_only([tmp_path / "b.fq"]) == b"1_1_1\t1\t24\n"
+    (tmp_path / "c.fq").write_bytes(rec + b"@r2#2_2_2/1\n")                                     # header, then nothing: empty read
+    assert parse_only([tmp_path / "c.fq"]) == b"1_1_1\t1\t24\n2_2_2\t1\t0\n"
+    (tmp_path / "d.fq").write_bytes(b"")
+    assert parse_only([tmp_path / "d.fq"]) == b""
+    r = run([CLASSIFY, "--hap0", "x", "--hap1", "y", "--read", tmp_path / "missing.fq"],
+            env=dict(os.environ, HAST_PARSE_ONLY="1"))
+    assert r.returncode == 1 and b"cannot open" in r.stderr
+
+
+def test_output_order_is_bytewise(tmp_path):
+    # std::map<std::string>: "0_0_0" < "10_1_1" < "1_2_3" because '0' (0x30) < '_' (0x5F)  
+    names = [b"1_2_3", b"10_1_1", b"0_0_0", b"Z", b"a", b"1_10_1", b"1_1_10"]
+    heads = [b"@r#%s/1" % n for n in names]
+    cases.write_fastq(tmp_path / "a.fq", heads, [b"ACGT" * 8] * len(names))
+    got = [ln.split(b"\t")[0] for ln in parse_only([tmp_path / "a.fq"]).splitlines()]
+    assert got == sorted(names) and got[:3] == [b"0_0_0", b"10_1_1", b"1_10_1"]
+
+
+def test_merge_result_matches_golden_and_reference():
+    d = GOLDEN / "merge"
+    args = json.loads((d / "cmd.txt").read_text())
+    r = run([MERGE] + args, cwd=d)
+    assert r.returncode == 0 and r.stdout == (d / "expected.tsv").read_bytes()
+    assert run([MERGE]).returncode == 255 and run([MERGE, "-i", "a.tsv"], cwd=d).returncode == 255   # no short -i
+    assert run([MERGE, "--input", "nope.tsv"], cwd=d).returncode == 255
+    ref = orc.ref_binary("mergeResult")
+    if ref is not None:
+        assert run([ref] + args, cwd=d).stdout == r.stdout
+
+
+def test_merge_result_intended_mode(tmp_path):
+    (tmp_path / "a.tsv").write_text("1_2_3\t1\t1\t3\n9_9_9\t0\t4\t1\n0_0_0\t-1\t7\t7\n")
+    (tmp_path / "b.tsv").write_text("1_2_3\t0\t4\t1\n")
+    r = run([MERGE, "--input", tmp_path / "a.tsv", "--input", tmp_path / "b.tsv", "--intended"])
+    assert r.stdout == b"0_0_0\t-1\t7\t7\n1_2_3\t0\t5\t4\n9_9_9\t0\t4\t1\n"
+    r = run([MERGE, "--input", tmp_path / "a.tsv", "--input", tmp_path / "b.tsv", "--intended", "--weight1", "2"])
+    assert b"1_2_3\t1\t5\t4\n" in r.stdout
+    out = tmp_path / "o.tsv"
+    assert orc.merge_result([tmp_path / "a.tsv", tmp_path / "b.tsv"], out, 1.0, 2.0, intended=True) == 0
+    assert out.read_bytes() == r.stdout
