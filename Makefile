@@ -20,7 +20,7 @@ HOST := hast_b200/host
 all: lib tools host oracle
 
 lib: $(LIB)
-$(LIB): $(CSRC)/hast_b200.cu $(CSRC)/kernels.cuh $(CSRC)/table.cuh $(CSRC)/kmer.cuh include/hast_b200.h
+$(LIB): $(CSRC)/hast_b200.cu $(CSRC)/kernels.cuh $(CSRC)/fused.cuh $(CSRC)/table.cuh $(CSRC)/kmer.cuh include/hast_b200.h
 	@mkdir -p hast_b200/lib
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared $< -o $@ -ldl 2> hast_b200/lib/ptxas.log || (cat hast_b200/lib/ptxas.log; exit 1)
 	@grep -E "registers|spill" hast_b200/lib/ptxas.log | sort | uniq -c | sort -rn | head -20 || true

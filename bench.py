@@ -227,6 +227,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--table-scale", type=float, default=1.0, help="expected_keys multiplier (sparser table)")
+    ap.add_argument("--kernel", type=int, default=1, choices=[0, 1],
+                    help="1 = pre-filtered fused kernel (default), 0 = direct table probe per position")
+    ap.add_argument("--filter-bits", type=int, default=16, help="pre-filter bits per key")
+    ap.add_argument("--filter-max-mib", type=int, default=64, help="pre-filter size cap (MiB)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "hast_b200" else args.warmup
     if args.impl == "reference":
@@ -280,6 +284,9 @@ def main():
     nb = trio.n_barcodes
 
     eng = Engine(local)
+    eng.set_option("kernel", args.kernel)
+    eng.set_option("filter_bits_per_key", args.filter_bits)
+    eng.set_option("filter_max_bytes", args.filter_max_mib << 20)
     n_keys = trio.pat.size + trio.mat.size
     eng.table_begin(spec.k, int(n_keys * args.table_scale))
     t0 = time.perf_counter()
@@ -289,7 +296,7 @@ def main():
     eng.table_erase_seq(b"TCTGCTGAGTCGAGAACGTCTCTGTGAGCCAAGGAGTTGCTCTGG")
     info = eng.table_info()
     t_table = time.perf_counter() - t0
-    log(f"rank {rank}: table {info.bytes / 2**20:.0f} MiB, {info.n_entries} entries, "
+    log(f"rank {rank}: table {info.bytes / 2**20:.0f} MiB + pre-filter {info.filter_bytes / 2**20:.1f} MiB, {info.n_entries} entries, "
         f"{info.n_overflow_buckets} overflow buckets, {info.n_displaced} displaced, built in {t_table:.2f}s")
     eng.reserve_barcodes(nb)
     if world > 1:
@@ -351,7 +358,7 @@ def main():
     gather = eng.gather_roofline(1 << 28, 4 << 30) if rank == 0 else None
     gather_tbl = eng.gather_roofline(1 << 28, info.bytes) if rank == 0 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "tile_kernel<MODE_CLASSIFY>", "launches_per_step": len(batches),
+                "traffic": traffic, "kernel": "classify_kernel" if args.kernel == 1 else "tile_kernel<MODE_CLASSIFY>", "launches_per_step": len(batches),
                 "ms_per_launch": ms_kernel / len(batches),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                 "lookups_per_s": lookups_step / (ms_kernel * 1e-3),
@@ -410,7 +417,7 @@ def main():
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": WORKLOAD_TEXT[args.workload], "k": spec.k, "read_len": L,
                            "pairs_per_gpu": P, "barcodes": nb, "table_keys": int(info.n_entries),
-                           "table_bytes": int(info.bytes), "sub_batches_per_step": len(batches),
+                           "table_bytes": int(info.bytes), "filter_bytes": int(info.filter_bytes), "sub_batches_per_step": len(batches),
                            "l2": "inputs (%.1f GB of reads per step) are larger than L2; the k-mer table is the "
                                  "workload's own hot state" % (n_reads * (L + 8) / 1e9),
                            "parallelism": f"dp{world}: reads sharded, table replicated, one ncclReduce of counts"},
@@ -418,7 +425,10 @@ def main():
                 "table_build_s": t_table,
                 "clocks": clk.summary(), "gpu_launches": int(gpu_launches),
                 "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-                "stats": {k: st[k] for k in ("reads_with_n", "extra_probes")}}
+                "stats": {"reads_with_n": st["reads_with_n"] // args.steps, "extra_probes": st["extra_probes"] // args.steps,
+                          "filter_pass_per_step": st["filter_pass"] // args.steps,
+                          "filter_pass_frac": st["filter_pass"] / max(1, st["lookups"]),
+                          "filter_bytes": int(info.filter_bytes), "kernel": args.kernel}}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -31,13 +31,14 @@ class HastError(RuntimeError):
 class TableInfo(C.Structure):
     _fields_ = [("k", C.c_int32), ("log2_buckets", C.c_int32), ("n_buckets", C.c_uint64),
                 ("bytes", C.c_uint64), ("n_entries", C.c_uint64), ("n_displaced", C.c_uint64),
-                ("n_overflow_buckets", C.c_uint64), ("size", C.c_uint64 * 2)]
+                ("n_overflow_buckets", C.c_uint64), ("size", C.c_uint64 * 2),
+                ("filter_bytes", C.c_uint64)]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("batches", "reads", "bases", "lookups", "reads_with_n", "reads_short",
-                 "extra_probes", "kernel_launches", "h2d_bytes", "d2h_bytes")]
+                 "extra_probes", "kernel_launches", "h2d_bytes", "d2h_bytes", "filter_pass")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -53,6 +54,7 @@ SIGNATURES = {
     "hast_destroy": (None, [_vp]),
     "hast_last_error": (C.c_char_p, [_vp]),
     "hast_device": (_i32, [_vp]),
+    "hast_set_option": (_i32, [_vp, C.c_char_p, C.c_int64]),
     "hast_host_alloc": (_i32, [C.POINTER(_vp), C.c_size_t]),
     "hast_host_free": (_i32, [_vp]),
     "hast_table_begin": (_i32, [_vp, _i32, _u64]),
@@ -149,6 +151,9 @@ class Engine:
     @property
     def handle(self):
         return self._ctx
+
+    def set_option(self, name: str, value: int):
+        self._ck(self.lib.hast_set_option(self._ctx, name.encode(), int(value)))
 
     # -- K1 ---------------------------------------------------------------
     def table_begin(self, k: int, expected_keys: int):

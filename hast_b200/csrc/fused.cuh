@@ -1,0 +1,339 @@
+// fused.cuh -- the fused read-classification kernel (K2 + K3 + K4), second generation.
+//
+// Replaces MultiThread::process_reads (classify.cpp:186-209): containN, every
+// canonical k-mer of the read (Kmer::chopRead2Kmer, kmer.h:169-194), the two
+// unordered_set finds per k-mer (classify.cpp:195-202) and IncrBarcodeHaps
+// (classify.cpp:52-56,203-206).
+//
+// What bounds it (measured on B200, profiles/microbench_r01.csv): an SM retires
+// ONE divergent 128-byte-line request per clock, i.e. 290 G random probes/s for
+// the whole chip when the probed structure is L2-resident, but only 38 G/s when
+// every probe is an HBM transaction.  ~99 % of the k-mer positions of a read are
+// in neither parent's set, so the kernel answers them from an L2-resident Bloom
+// pre-filter (one 8-byte probe per position) and sends only the few positions
+// that pass (members + ~1-5 % false positives) to the exact table in HBM
+// (table.cuh; one 32-byte sector per probe).  The filter only ever says "maybe":
+// every vote still comes from an exact match in the table, so results stay
+// bit-identical to the reference.
+//
+// Per tile of kReadsPerTile reads, one CTA:
+//   (a) 128-bit streaming loads of the read bytes (L2 evict-first) -> 2-bit
+//       MSB-first words in shared memory; 'N' bytes flagged in a bit mask
+//   (b) one thread per read: containN, mark the positions that start no k-mer
+//   (c) one thread per 16-position chunk: the forward and reverse-complement
+//       k-mers ROLL in registers (kmer.h:109-127 does the same on 128-bit
+//       words), min -> hash -> one 8-byte filter load per valid position, eight
+//       loads in flight per thread; passing positions are appended to a
+//       shared-memory queue (warp-aggregated)
+//   (d) the queue is drained by all threads: exact probe of the table, hits add
+//       their tag bits to the owning read's vote word
+//   (e) one thread per read: votes -> per-barcode counters, aggregated by
+//       barcode across the warp before any global atomic
+#pragma once
+#include <cstdint>
+#include "kernels.cuh"
+
+namespace hast {
+
+constexpr int kQueueCap = 8192;                          // passing positions buffered per CTA
+constexpr int kChunk = 16;                               // positions per thread per sweep (= bases per packed word)
+constexpr int kSweep = kTileThreads * kChunk;            // positions per CTA sweep
+
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+// one filter word; keep it in L2 ahead of the streaming read bytes
+__device__ __forceinline__ uint64_t load_filter(const uint64_t* p, uint64_t pol) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+// 16 read bytes, used once: do not let them push the filter / table out of L2
+__device__ __forceinline__ uint4 load_stream16_ef(const uint8_t* p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+
+__global__ void __launch_bounds__(kTileThreads, 4)
+classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_barcodes,
+                DevStats* __restrict__ stats) {
+    __shared__ uint32_t s_off[kReadsPerTile + 1];
+    __shared__ uint32_t s_votes[kReadsPerTile];
+    __shared__ uint32_t s_packed[kTileWords + 4];
+    __shared__ uint32_t s_bad[kTileWords / 2 + 2];
+    __shared__ uint16_t s_queue[kQueueCap];
+    __shared__ uint32_t s_qn;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const int k = t.k;
+    const uint64_t kmask = t.kmask;
+    const uint32_t n_tiles = (b.n_reads + kReadsPerTile - 1) / kReadsPerTile;
+    const uint64_t pol_last = policy_evict_last(), pol_first = policy_evict_first();
+
+    // rolling-window constants: the chunk at base position p starts from the k-1
+    // bases p .. p+k-2 and then takes in base p+k-1+j for its j-th k-mer
+    const int km1 = k - 1;
+    const uint64_t mask_km1 = kmer_mask(km1);
+    const uint32_t fwd_init_shift = 64u - 2u * (uint32_t)km1;   // 64 when k == 1 (handled below)
+    const uint32_t rc_shift = 2u * (uint32_t)km1;
+    const uint32_t nxt_word = (uint32_t)km1 >> 4, nxt_sh = ((uint32_t)km1 & 15u) * 2u;
+
+    unsigned long long st_lookups = 0, st_n = 0, st_short = 0, st_long = 0, st_badbc = 0;
+    uint32_t st_extra = 0, st_pass = 0;
+
+    if (tid == 0) s_qn = 0;
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t r0 = tile * kReadsPerTile;
+        const uint32_t R = min((uint32_t)kReadsPerTile, b.n_reads - r0);
+        for (uint32_t i = tid; i <= R; i += kTileThreads) s_off[i] = b.read_off[r0 + i];
+        for (uint32_t i = tid; i < R; i += kTileThreads) s_votes[i] = 0;
+        __syncthreads();
+
+        uint32_t ra = 0;
+        while (ra < R) {
+            // reads [ra, rb) of the tile whose bytes fit one pass
+            const uint32_t lo = s_off[ra] & ~15u;
+            uint32_t rb;
+            {
+                uint32_t a = ra, c = R;                    // largest rb with s_off[rb] - lo <= cap
+                while (a < c) {
+                    const uint32_t m = (a + c + 1) >> 1;
+                    if (s_off[m] - lo <= (uint32_t)kTileCapBytes) a = m; else c = m - 1;
+                }
+                rb = a;
+            }
+            if (rb == ra) {                                // a single read larger than a pass
+                if (tid == 0) ++st_long;
+                ra += 1;
+                continue;
+            }
+            const uint32_t hi = s_off[rb];
+            const uint32_t nseg = (hi - lo + 15u) >> 4;
+
+            for (uint32_t i = tid; i < (nseg >> 1) + 2; i += kTileThreads) s_bad[i] = 0;
+            __syncthreads();
+
+            // (a) pack
+            for (uint32_t seg = tid; seg < nseg + 4; seg += kTileThreads) {
+                uint32_t word = 0;
+                if (seg < nseg) {
+                    const uint64_t g = (uint64_t)lo + 16ull * seg;
+                    uint4 v;
+                    if (g + 16 <= b.n_bases) {
+                        v = load_stream16_ef(b.bases + g, pol_first);
+                    } else {                               // last, partial segment of the batch
+                        uint32_t w[4] = {0, 0, 0, 0};
+                        for (uint32_t j = 0; j < 16 && g + j < b.n_bases; ++j)
+                            w[j >> 2] |= (uint32_t)b.bases[g + j] << (8 * (j & 3));
+                        v = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    word = pack16(v);
+                    if (any_N4(v.x) | any_N4(v.y) | any_N4(v.z) | any_N4(v.w)) {
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        uint32_t m16 = 0;
+                        for (uint32_t j = 0; j < 16; ++j)
+                            if (((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) == 'N') m16 |= 1u << j;
+                        atomicOr(&s_bad[seg >> 1], m16 << ((seg & 1u) * 16u));
+                    }
+                }
+                s_packed[seg] = word;
+            }
+            __syncthreads();
+
+            // (b) per read: containN (classify.cpp:182-185), positions that start no k-mer
+            for (uint32_t r = ra + tid; r < rb; r += kTileThreads) {
+                const uint32_t s = s_off[r] - lo, e = s_off[r + 1] - lo, L = e - s;
+                if (any_bits(s_bad, s, e)) {               // classify.cpp:190-193: no votes at all
+                    ++st_n;
+                    set_bits(s_bad, s, e);
+                } else if (L < (uint32_t)k) {              // kmer.h:171 assert in the reference
+                    ++st_short;
+                    set_bits(s_bad, s, e);
+                } else {
+                    st_lookups += L - (uint32_t)k + 1u;
+                    set_bits(s_bad, e - (uint32_t)k + 1u, e);
+                }
+            }
+            // positions before the first read of the pass and after the last one
+            if (tid == 0) {
+                set_bits(s_bad, 0, s_off[ra] - lo);
+                set_bits(s_bad, hi - lo, nseg * 16u);
+            }
+            __syncthreads();
+
+            // (c) filter sweep: thread <-> packed word (16 positions)
+            for (uint32_t wbase = 0; wbase < nseg; wbase += kTileThreads) {
+                const uint32_t wi = wbase + tid;
+                uint32_t pass = 0;
+                uint32_t valid = 0;
+                if (wi < nseg) valid = ~(s_bad[wi >> 1] >> ((wi & 1u) * 16u)) & 0xFFFFu;
+                if (valid) {
+                    const uint32_t w0 = s_packed[wi], w1 = s_packed[wi + 1];
+                    const uint32_t nxt = __funnelshift_l(s_packed[wi + nxt_word + 1], s_packed[wi + nxt_word], nxt_sh);
+                    const uint64_t x = ((uint64_t)w0 << 32) | w1;
+                    uint64_t fwd = km1 ? (x >> fwd_init_shift) : 0ull;
+                    uint64_t rcv = revcomp_top(x, mask_km1) << 2;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint64_t fw[8];
+                        uint32_t hh[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = half * 8 + u;
+                            const uint32_t c = (nxt >> (30 - 2 * j)) & 3u;
+                            fwd = ((fwd << 2) | c) & kmask;
+                            rcv = (rcv >> 2) | ((uint64_t)(c ^ 2u) << rc_shift);
+                            const uint64_t canon = fwd < rcv ? fwd : rcv;
+                            hh[u] = filter_hash(canon);
+                            fw[u] = 0ull;
+                            if ((valid >> j) & 1u) fw[u] = load_filter(t.filt + (hh[u] >> t.filt_shift), pol_last);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const uint32_t hit = ((uint32_t)fw[u] >> (hh[u] & 31u)) &
+                                                 ((uint32_t)(fw[u] >> 32) >> ((hh[u] >> 5) & 31u)) & 1u;
+                            pass |= hit << (half * 8 + u);
+                        }
+                    }
+                }
+                // append the passing positions to the queue: one shared atomic per warp
+                const uint32_t cnt = __popc(pass);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= (uint32_t)o) incl += v;
+                }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                uint32_t qend = 0;                         // queue fill after this warp's append
+                if (total) {
+                    uint32_t qbase = 0;
+                    if (lane == 31) qbase = atomicAdd(&s_qn, total);
+                    qbase = __shfl_sync(0xFFFFFFFFu, qbase, 31);
+                    qend = qbase + total;
+                    uint32_t q = qbase + incl - cnt;
+                    st_pass += cnt;
+                    while (pass) {
+                        const uint32_t j = __ffs(pass) - 1;
+                        pass &= pass - 1;
+                        s_queue[q++] = (uint16_t)(wi * 16u + j);
+                    }
+                }
+                // (d) drain when another sweep might not fit, and after the last sweep.  The
+                // warp that appended last saw the final fill, so the OR over the CTA is exact
+                // and uniform (one barrier, no racy re-read of s_qn).
+                const bool last = wbase + kTileThreads >= nseg;
+                if (__syncthreads_or(last || qend + kSweep > (uint32_t)kQueueCap)) {
+                    const uint32_t qn = s_qn;
+                    __syncthreads();                       // everyone holds qn before it is reset
+                    if (tid == 0) s_qn = 0;
+                    for (uint32_t i0 = 0; i0 < qn; i0 += kTileThreads * 2) {
+                        uint32_t p[2];
+                        uint64_t want[2];
+                        Bucket bk[2];
+                        uint32_t bucket[2];
+                        bool on[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const uint32_t i = i0 + u * kTileThreads + tid;
+                            on[u] = i < qn;
+                            p[u] = on[u] ? s_queue[i] : 0u;
+                            const uint64_t canon = canonical_at(s_packed, p[u], k, kmask);
+                            const uint64_t h = table_hash(canon, k, kmask);
+                            bucket[u] = (uint32_t)(h >> t.rem_bits);
+                            want[u] = (h & t.rem_mask) << 4;
+                            bk[u].s0 = bk[u].s1 = bk[u].s2 = bk[u].s3 = 0ull;
+                            if (on[u]) bk[u] = load_bucket(t.slots + (size_t)bucket[u] * kSlotsPerBucket);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            bool found;
+                            uint32_t tag = match_bucket(bk[u], want[u], found);
+                            if (on[u] && !found && (bk[u].s0 & 1ull)) {       // overflowed home bucket
+                                uint32_t bkt = bucket[u];
+                                uint64_t w = want[u];
+                                for (int d = 1; d <= kMaxDisp; ++d) {
+                                    bkt = (bkt + 1) & t.bucket_mask;
+                                    w += 1;
+                                    const Bucket nb = load_bucket(t.slots + (size_t)bkt * kSlotsPerBucket);
+                                    ++st_extra;
+                                    tag = match_bucket(nb, w, found);
+                                    if (found || !(nb.s0 & 1ull)) break;
+                                }
+                            }
+                            if (on[u] && tag) {
+                                // which read owns position p: s_off[r] <= lo + p < s_off[r+1]
+                                const uint32_t gp = lo + p[u];
+                                uint32_t a = ra, c = rb - 1;
+                                while (a < c) {
+                                    const uint32_t m = (a + c + 1) >> 1;
+                                    if (s_off[m] <= gp) a = m; else c = m - 1;
+                                }
+                                atomicAdd(&s_votes[a], (tag & 1u) | ((tag >> 1) << 16));
+                            }
+                        }
+                    }
+                    __syncthreads();                       // queue consumed, s_qn reset: next sweep may append
+                }
+            }
+            __syncthreads();
+            ra = rb;
+        }
+
+        // (e) votes -> per-barcode counters (IncrBarcodeHaps, classify.cpp:203-206)
+        for (uint32_t rbase = 0; rbase < R; rbase += kTileThreads) {
+            const uint32_t r = rbase + tid;
+            const uint32_t v = r < R ? s_votes[r] : 0u;
+            const unsigned voters = __ballot_sync(0xFFFFFFFFu, v != 0u);
+            if (v) {
+                const uint32_t bc = b.barcode_id[r0 + r];
+                int v0 = (int)(v & 0xFFFFu), v1 = (int)(v >> 16);
+                const unsigned peers = __match_any_sync(voters, bc);
+                const int leader = __ffs(peers) - 1;
+                int s0 = 0, s1 = 0;
+                for (unsigned m = peers; m; m &= m - 1) {
+                    const int src = __ffs(m) - 1;
+                    s0 += __shfl_sync(peers, v0, src);
+                    s1 += __shfl_sync(peers, v1, src);
+                }
+                if ((int)lane == leader) {
+                    if (bc < n_barcodes) {
+                        if (s0) atomicAdd(&counts[2ull * bc], s0);
+                        if (s1) atomicAdd(&counts[2ull * bc + 1], s1);
+                    } else {
+                        ++st_badbc;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // per-warp flush of the statistics
+    for (int o = 16; o > 0; o >>= 1) {
+        st_lookups += __shfl_xor_sync(0xFFFFFFFFu, st_lookups, o);
+        st_n += __shfl_xor_sync(0xFFFFFFFFu, st_n, o);
+        st_short += __shfl_xor_sync(0xFFFFFFFFu, st_short, o);
+        st_long += __shfl_xor_sync(0xFFFFFFFFu, st_long, o);
+        st_badbc += __shfl_xor_sync(0xFFFFFFFFu, st_badbc, o);
+        st_extra += __shfl_xor_sync(0xFFFFFFFFu, st_extra, o);
+        st_pass += __shfl_xor_sync(0xFFFFFFFFu, st_pass, o);
+    }
+    if (lane == 0) {
+        if (st_lookups) atomicAdd(&stats->lookups, st_lookups);
+        if (st_n) atomicAdd(&stats->reads_with_n, st_n);
+        if (st_short) atomicAdd(&stats->reads_short, st_short);
+        if (st_long) atomicAdd(&stats->reads_too_long, st_long);
+        if (st_badbc) atomicAdd(&stats->bad_barcode, st_badbc);
+        if (st_extra) atomicAdd(&stats->extra_probes, (unsigned long long)st_extra);
+        if (st_pass) atomicAdd(&stats->filter_pass, (unsigned long long)st_pass);
+    }
+}
+
+}  // namespace hast

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "fused.cuh"
 
 using namespace hast;
 
@@ -105,6 +106,12 @@ struct hast_ctx {
     int nranks = 1, rank = 0;
 
     int tile_blocks = 0;                  // persistent grid of the tile kernels
+    int fused_blocks = 0;                 // persistent grid of classify_kernel
+    uint64_t filt_words = 0;
+    // options (hast_set_option)
+    int64_t opt_kernel = 1;               // 1 = classify_kernel (pre-filter), 0 = tile_kernel<MODE_CLASSIFY> (direct probe)
+    int64_t opt_filter_bits_per_key = 16;
+    int64_t opt_filter_max_bytes = (int64_t)64 << 20;
     std::string err;
 };
 
@@ -154,7 +161,10 @@ int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv, uint64_t* d_kmers,
     const uint32_t n_tiles = (bv.n_reads + kReadsPerTile - 1) / kReadsPerTile;
     if (!n_tiles) return HAST_OK;
     const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->tile_blocks);
-    if (mode == MODE_CLASSIFY)
+    if (mode == MODE_CLASSIFY && ctx->opt_kernel == 1)
+        classify_kernel<<<(int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->fused_blocks), kTileThreads, 0, ctx->cs>>>(
+            ctx->tv, bv, ctx->d_counts, (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull), ctx->d_stats);
+    else if (mode == MODE_CLASSIFY)
         tile_kernel<MODE_CLASSIFY><<<grid, kTileThreads, 0, ctx->cs>>>(
             ctx->tv, bv, ctx->d_counts, (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull),
             ctx->d_stats, nullptr, nullptr);
@@ -210,8 +220,11 @@ int hast_create(int device, hast_ctx** out) {
     CU_NEW(cudaMemset(ctx->d_stats, 0, sizeof(DevStats)));
     int per_sm = 0;
     CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel<MODE_CLASSIFY>, kTileThreads, 0));
+    int per_sm_f = 0;
+    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, classify_kernel, kTileThreads, 0));
 #undef CU_NEW
     ctx->tile_blocks = std::max(1, per_sm) * ctx->sm_count;
+    ctx->fused_blocks = std::max(1, per_sm_f) * ctx->sm_count;
     *out = ctx;
     return HAST_OK;
 }
@@ -227,6 +240,7 @@ void hast_destroy(hast_ctx* ctx) {
         if (s.done) cudaEventDestroy(s.done);
     }
     cudaFree(ctx->tv.slots);
+    cudaFree(ctx->tv.filt);
     cudaFree(ctx->d_counts);
     cudaFree(ctx->d_reduced);
     cudaFree(ctx->d_stats);
@@ -236,6 +250,24 @@ void hast_destroy(hast_ctx* ctx) {
     if (ctx->cs) cudaStreamDestroy(ctx->cs);
     if (ctx->hs) cudaStreamDestroy(ctx->hs);
     delete ctx;
+}
+
+int hast_set_option(hast_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return fail(ctx, HAST_E_ARG, "NULL argument");
+    const std::string n(name);
+    if (n == "kernel") {
+        if (value != 0 && value != 1) return fail(ctx, HAST_E_ARG, "kernel: 0 (direct probe) or 1 (pre-filter)");
+        ctx->opt_kernel = value;
+    } else if (n == "filter_bits_per_key") {
+        if (value < 1 || value > 64) return fail(ctx, HAST_E_ARG, "filter_bits_per_key: 1..64");
+        ctx->opt_filter_bits_per_key = value;
+    } else if (n == "filter_max_bytes") {
+        if (value < 128) return fail(ctx, HAST_E_ARG, "filter_max_bytes: >= 128");
+        ctx->opt_filter_max_bytes = value;
+    } else {
+        return fail(ctx, HAST_E_ARG, "unknown option: " + n);
+    }
+    return HAST_OK;
 }
 
 int hast_host_alloc(void** ptr, size_t bytes) {
@@ -257,6 +289,7 @@ int hast_table_begin(hast_ctx* ctx, int k, uint64_t expected_keys) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->cs));
     if (ctx->tv.slots) { CU(cudaFree(ctx->tv.slots)); ctx->tv.slots = nullptr; }
+    if (ctx->tv.filt) { CU(cudaFree(ctx->tv.filt)); ctx->tv.filt = nullptr; }
     ctx->table_ready = false;
     // load factor <= 0.5 over 4-slot buckets => at least expected/2 buckets, power of two
     int b = 4;
@@ -275,6 +308,15 @@ int hast_table_begin(hast_ctx* ctx, int k, uint64_t expected_keys) {
     ctx->tv.rem_bits = 2 * k - b;
     ctx->tv.rem_mask = ctx->tv.rem_bits ? (((uint64_t)1 << ctx->tv.rem_bits) - 1) : 0;
     ctx->tv.bucket_mask = (uint32_t)(ctx->n_buckets - 1);
+    // pre-filter: opt_filter_bits_per_key bits per expected key, power of two words, capped so that it
+    // stays L2-resident (fused.cuh); 2^4 .. 2^26 words
+    int fb = 4;
+    while (fb < 26 && ((uint64_t)64 << fb) < expected_keys * (uint64_t)ctx->opt_filter_bits_per_key) ++fb;
+    while (fb > 4 && ((uint64_t)8 << fb) > (uint64_t)ctx->opt_filter_max_bytes) --fb;
+    ctx->filt_words = (uint64_t)1 << fb;
+    CU(cudaMalloc(&ctx->tv.filt, ctx->filt_words * 8));
+    CU(cudaMemsetAsync(ctx->tv.filt, 0, ctx->filt_words * 8, ctx->cs));
+    ctx->tv.filt_shift = 32 - fb;
     CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->cs));
     if (ctx->d_counts) CU(cudaMemsetAsync(ctx->d_counts, 0, ctx->cap_barcodes * 2 * sizeof(int32_t), ctx->cs));
     ctx->table_ready = true;
@@ -393,6 +435,7 @@ int hast_table_info_get(hast_ctx* ctx, hast_table_info* out) {
     out->n_overflow_buckets = tc.overflow_buckets;
     out->size[0] = tc.size0;
     out->size[1] = tc.size1;
+    out->filter_bytes = ctx->filt_words * 8;
     return HAST_OK;
 }
 
@@ -405,12 +448,17 @@ int hast_table_clone(hast_ctx* dst, hast_ctx* src) {
     CU(cudaSetDevice(dst->device));
     CU(cudaStreamSynchronize(dst->cs));
     if (dst->tv.slots) { CU(cudaFree(dst->tv.slots)); dst->tv.slots = nullptr; }
+    if (dst->tv.filt) { CU(cudaFree(dst->tv.filt)); dst->tv.filt = nullptr; }
     const size_t bytes = src->n_buckets * kSlotsPerBucket * 8;
-    uint64_t* p = nullptr;
+    uint64_t *p = nullptr, *f = nullptr;
     CU(cudaMalloc(&p, bytes));
+    CU(cudaMalloc(&f, src->filt_words * 8));
     CU(cudaMemcpyPeer(p, dst->device, src->tv.slots, src->device, bytes));
+    CU(cudaMemcpyPeer(f, dst->device, src->tv.filt, src->device, src->filt_words * 8));
     dst->tv = src->tv;
     dst->tv.slots = p;
+    dst->tv.filt = f;
+    dst->filt_words = src->filt_words;
     dst->n_buckets = src->n_buckets;
     dst->table_ready = true;
     return HAST_OK;
@@ -529,6 +577,7 @@ int hast_stats_get(hast_ctx* ctx, hast_stats* out) {
     out->reads_with_n = ds.reads_with_n;
     out->reads_short = ds.reads_short;
     out->extra_probes = ds.extra_probes;
+    out->filter_pass = ds.filter_pass;
     return HAST_OK;
 }
 

@@ -29,6 +29,7 @@ struct DevStats {
     unsigned long long table_full;
     unsigned long long reads_too_long;
     unsigned long long bad_barcode;
+    unsigned long long filter_pass;
 };
 
 struct BatchView {
@@ -326,6 +327,12 @@ __device__ __forceinline__ void table_insert(const TableView& t, uint64_t canon,
     uint32_t bucket = (uint32_t)(h >> t.rem_bits);
     const uint64_t rem4 = (h & t.rem_mask) << 4;
     const uint64_t tagbits = (uint64_t)(1u << parent) << 1;
+    {   // pre-filter first: a key must never be in the table without its filter bits
+        const uint32_t fh = filter_hash(canon);
+        unsigned long long* fw = (unsigned long long*)(t.filt + (fh >> t.filt_shift));
+        const unsigned long long bits = filter_bits(fh);
+        if ((*(volatile unsigned long long*)fw & bits) != bits) atomicOr(fw, bits);
+    }
     for (int d = 0; d <= kMaxDisp; ++d) {
         const uint64_t want = rem4 | (uint64_t)d;
         unsigned long long* base = (unsigned long long*)(t.slots + (size_t)bucket * kSlotsPerBucket);

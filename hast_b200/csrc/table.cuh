@@ -39,6 +39,10 @@ struct TableView {
     uint32_t bucket_mask;   // n_buckets - 1
     int32_t k;
     int32_t rem_bits;       // 2k - b, 0..57
+    // Bloom pre-filter over every key ever inserted (fused.cuh): 2^(32-filt_shift)
+    // 64-bit words, two bits per key, one in each half of the key's word
+    uint64_t* filt;
+    uint32_t filt_shift;
 };
 
 // multiply / xor-shift / multiply, every step a bijection of Z/2^(2k)
@@ -47,6 +51,19 @@ __host__ __device__ __forceinline__ uint64_t table_hash(uint64_t key, int k, uin
     h ^= h >> k;
     h = (h * kHashC2) & kmask;
     return h;
+}
+
+// 32 well-mixed bits of a canonical k-mer for the pre-filter: top bits pick the
+// word, bits 0-4 / 5-9 pick the bit inside the low / high half of the word
+__host__ __device__ __forceinline__ uint32_t filter_hash(uint64_t canon) {
+    uint32_t m = (uint32_t)canon * 0x9E3779B1u + (uint32_t)(canon >> 32) * 0x85EBCA77u;
+    m ^= m >> 15;
+    m *= 0xC2B2AE3Du;
+    m ^= m >> 13;
+    return m;
+}
+__host__ __device__ __forceinline__ uint64_t filter_bits(uint32_t h) {
+    return (1ull << (h & 31u)) | (1ull << (32u + ((h >> 5) & 31u)));
 }
 
 #ifdef __CUDACC__

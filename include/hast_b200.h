@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HAST_ABI_VERSION 1
+#define HAST_ABI_VERSION 2
 
 #define HAST_OK            0
 #define HAST_E_ARG        -1   /* bad argument                                            */
@@ -49,6 +49,7 @@ typedef struct hast_table_info {
     uint64_t n_displaced;      /* entries that live outside their home bucket             */
     uint64_t n_overflow_buckets;
     uint64_t size[2];          /* g_kmers[i].size() after erases                          */
+    uint64_t filter_bytes;     /* L2-resident Bloom pre-filter in front of the table      */
 } hast_table_info;
 
 typedef struct hast_stats {
@@ -62,6 +63,7 @@ typedef struct hast_stats {
     uint64_t kernel_launches;  /* launches of this library's own kernels                  */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
+    uint64_t filter_pass;      /* lookups the pre-filter sent on to the exact table       */
 } hast_stats;
 
 /* ---- library / context ------------------------------------------------- */
@@ -72,6 +74,11 @@ int          hast_create(int device, hast_ctx **out);
 void         hast_destroy(hast_ctx *ctx);
 const char  *hast_last_error(const hast_ctx *ctx);      /* ctx may be NULL */
 int          hast_device(const hast_ctx *ctx);
+/* Tuning knobs, set before hast_table_begin: "kernel" (1 = pre-filtered fused
+ * kernel, default; 0 = direct table probe per position), "filter_bits_per_key"
+ * (default 16), "filter_max_bytes" (default 64 MiB: the filter is meant to stay
+ * L2-resident).  None of them changes any result.                              */
+int          hast_set_option(hast_ctx *ctx, const char *name, int64_t value);
 /* pinned host memory for batch buffers */
 int          hast_host_alloc(void **ptr, size_t bytes);
 int          hast_host_free(void *ptr);

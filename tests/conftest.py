@@ -44,9 +44,12 @@ def _built():
     yield
 
 
-@pytest.fixture(scope="session")
-def engine():
+@pytest.fixture(scope="session", params=[1, 0], ids=["prefilter", "direct"])
+def engine(request):
+    """One context per fused-kernel variant: 1 = Bloom pre-filter + exact table (default),
+    0 = direct table probe per position.  Both must be bit-identical to the oracle."""
     from hast_b200.capi import Engine
     e = Engine(0)
+    e.set_option("kernel", request.param)
     yield e
     e.close()

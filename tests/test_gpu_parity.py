@@ -188,6 +188,25 @@ def test_table_under_pressure(engine):
     assert st["extra_probes"] > 0
 
 
+def test_saturated_filter_queue_drains(engine):
+    """A pre-filter far too small for the key set passes (almost) every position, so the
+    shared-memory queue fills and drains every sweep; the exact table still decides."""
+    case = cases.adversarial_case(21, 3000, seed=13, min_len=80, max_len=400)
+    o, _ = build_oracle(case)
+    bases, off = cases.flatten(case["reads"])
+    want, lookups = o.classify_batch(bases, off, case["bc_ids"], len(case["bc_names"]))
+    try:
+        engine.set_option("filter_max_bytes", 128)
+        build_table(engine, case)
+        assert engine.table_info().filter_bytes == 128
+        got, st = run_fused(engine, case)
+    finally:
+        engine.set_option("filter_max_bytes", 64 << 20)
+    assert (got == want).all() and st["lookups"] == lookups
+    if st["filter_pass"]:                              # the pre-filtered kernel
+        assert st["filter_pass"] > 0.9 * lookups
+
+
 @pytest.fixture(scope="module")
 def trio_small():
     return synth.make_trio(synth.config("small"))
