@@ -55,6 +55,8 @@ def workload_spec(name: str, rank: int):
 
 WORKLOAD_TEXT = {
     "cfg2": "configs[1]: synthetic 100 Mbp diploid trio (0.1% het), k=21, 20M stLFR 100bp read pairs / 500k barcodes",
+    "cfg3t": "configs[2] table scale: human-size parent-unique k-mer lists (62 M keys: the cfg2 trio + random decoys), "
+             "k=21, 20M stLFR 100bp read pairs / 500k barcodes per GPU",
     "cfg1": "configs[0]: synthetic 5 Mbp diploid trio (0.1% het), k=21, 200k stLFR 100bp read pairs / 10k barcodes",
     "small": "dev: 500 kbp trio, 20k pairs / 1k barcodes",
 }

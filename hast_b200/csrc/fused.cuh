@@ -35,9 +35,21 @@
 
 namespace hast {
 
-constexpr int kQueueCap = 8192;                          // passing positions buffered per CTA
+constexpr int kQueueCap = 6144;                          // passing positions buffered per CTA
 constexpr int kChunk = 16;                               // positions per thread per sweep (= bases per packed word)
-constexpr int kSweep = kTileThreads * kChunk;            // positions per CTA sweep
+constexpr int kDrainUnroll = 4;                          // exact probes in flight per thread while draining
+
+// hit at global base offset gp: add the tag bits to the vote word of the read that owns it,
+// s_off[r] <= gp < s_off[r+1] with r in [ra, rb)
+__device__ __forceinline__ void vote(uint32_t* s_votes, const uint32_t* s_off, uint32_t ra, uint32_t rb,
+                                     uint32_t gp, uint32_t tag) {
+    uint32_t a = ra, c = rb - 1;
+    while (a < c) {
+        const uint32_t m = (a + c + 1) >> 1;
+        if (s_off[m] <= gp) a = m; else c = m - 1;
+    }
+    atomicAdd(&s_votes[a], (tag & 1u) | ((tag >> 1) << 16));
+}
 
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
@@ -59,6 +71,8 @@ __device__ __forceinline__ uint4 load_stream16_ef(const uint8_t* p, uint64_t pol
     return v;
 }
 
+// KT > 0: k is the compile-time constant KT (shift amounts fold into immediates); KT == 0: any k in 1..32.
+template <int KT>
 __global__ void __launch_bounds__(kTileThreads, 4)
 classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_barcodes,
                 DevStats* __restrict__ stats) {
@@ -70,8 +84,8 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
     __shared__ uint32_t s_qn;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const int k = t.k;
-    const uint64_t kmask = t.kmask;
+    const int k = KT ? KT : t.k;
+    const uint64_t kmask = KT ? kmer_mask(KT) : t.kmask;
     const uint32_t n_tiles = (b.n_reads + kReadsPerTile - 1) / kReadsPerTile;
     const uint64_t pol_last = policy_evict_last(), pol_first = policy_evict_first();
 
@@ -182,7 +196,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         uint64_t fw[8];
-                        uint32_t hh[8];
+                        uint32_t hb[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const int j = half * 8 + u;
@@ -190,19 +204,21 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                             fwd = ((fwd << 2) | c) & kmask;
                             rcv = (rcv >> 2) | ((uint64_t)(c ^ 2u) << rc_shift);
                             const uint64_t canon = fwd < rcv ? fwd : rcv;
-                            hh[u] = filter_hash(canon);
+                            const FilterHash fh = filter_hash(canon);
+                            hb[u] = fh.bits;
                             fw[u] = 0ull;
-                            if ((valid >> j) & 1u) fw[u] = load_filter(t.filt + (hh[u] >> t.filt_shift), pol_last);
+                            if ((valid >> j) & 1u) fw[u] = load_filter(t.filt + (fh.word >> t.filt_shift), pol_last);
                         }
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const uint32_t hit = ((uint32_t)fw[u] >> (hh[u] & 31u)) &
-                                                 ((uint32_t)(fw[u] >> 32) >> ((hh[u] >> 5) & 31u)) & 1u;
+                            const uint32_t hit = ((uint32_t)fw[u] >> (hb[u] >> 27)) &
+                                                 ((uint32_t)(fw[u] >> 32) >> ((hb[u] >> 22) & 31u)) & 1u;
                             pass |= hit << (half * 8 + u);
                         }
                     }
                 }
-                // append the passing positions to the queue: one shared atomic per warp
+                // append the passing positions to the queue: one shared atomic per warp; no
+                // CTA barrier between sweeps, the warps drift apart and overlap each other's loads
                 const uint32_t cnt = __popc(pass);
                 uint32_t incl = cnt;
 #pragma unroll
@@ -211,78 +227,72 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                     if (lane >= (uint32_t)o) incl += v;
                 }
                 const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                uint32_t qend = 0;                         // queue fill after this warp's append
                 if (total) {
                     uint32_t qbase = 0;
                     if (lane == 31) qbase = atomicAdd(&s_qn, total);
                     qbase = __shfl_sync(0xFFFFFFFFu, qbase, 31);
-                    qend = qbase + total;
                     uint32_t q = qbase + incl - cnt;
                     st_pass += cnt;
                     while (pass) {
                         const uint32_t j = __ffs(pass) - 1;
                         pass &= pass - 1;
-                        s_queue[q++] = (uint16_t)(wi * 16u + j);
-                    }
-                }
-                // (d) drain when another sweep might not fit, and after the last sweep.  The
-                // warp that appended last saw the final fill, so the OR over the CTA is exact
-                // and uniform (one barrier, no racy re-read of s_qn).
-                const bool last = wbase + kTileThreads >= nseg;
-                if (__syncthreads_or(last || qend + kSweep > (uint32_t)kQueueCap)) {
-                    const uint32_t qn = s_qn;
-                    __syncthreads();                       // everyone holds qn before it is reset
-                    if (tid == 0) s_qn = 0;
-                    for (uint32_t i0 = 0; i0 < qn; i0 += kTileThreads * 2) {
-                        uint32_t p[2];
-                        uint64_t want[2];
-                        Bucket bk[2];
-                        uint32_t bucket[2];
-                        bool on[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const uint32_t i = i0 + u * kTileThreads + tid;
-                            on[u] = i < qn;
-                            p[u] = on[u] ? s_queue[i] : 0u;
-                            const uint64_t canon = canonical_at(s_packed, p[u], k, kmask);
-                            const uint64_t h = table_hash(canon, k, kmask);
-                            bucket[u] = (uint32_t)(h >> t.rem_bits);
-                            want[u] = (h & t.rem_mask) << 4;
-                            bk[u].s0 = bk[u].s1 = bk[u].s2 = bk[u].s3 = 0ull;
-                            if (on[u]) bk[u] = load_bucket(t.slots + (size_t)bucket[u] * kSlotsPerBucket);
+                        const uint32_t pos = wi * 16u + j;
+                        if (q < (uint32_t)kQueueCap) {
+                            s_queue[q] = (uint16_t)pos;
+                        } else {                           // queue full (saturated filter): resolve in place
+                            const uint32_t tag = table_probe(t, canonical_at(s_packed, pos, k, kmask), st_extra);
+                            if (tag) vote(s_votes, s_off, ra, rb, lo + pos, tag);
                         }
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            bool found;
-                            uint32_t tag = match_bucket(bk[u], want[u], found);
-                            if (on[u] && !found && (bk[u].s0 & 1ull)) {       // overflowed home bucket
-                                uint32_t bkt = bucket[u];
-                                uint64_t w = want[u];
-                                for (int d = 1; d <= kMaxDisp; ++d) {
-                                    bkt = (bkt + 1) & t.bucket_mask;
-                                    w += 1;
-                                    const Bucket nb = load_bucket(t.slots + (size_t)bkt * kSlotsPerBucket);
-                                    ++st_extra;
-                                    tag = match_bucket(nb, w, found);
-                                    if (found || !(nb.s0 & 1ull)) break;
-                                }
-                            }
-                            if (on[u] && tag) {
-                                // which read owns position p: s_off[r] <= lo + p < s_off[r+1]
-                                const uint32_t gp = lo + p[u];
-                                uint32_t a = ra, c = rb - 1;
-                                while (a < c) {
-                                    const uint32_t m = (a + c + 1) >> 1;
-                                    if (s_off[m] <= gp) a = m; else c = m - 1;
-                                }
-                                atomicAdd(&s_votes[a], (tag & 1u) | ((tag >> 1) << 16));
-                            }
-                        }
+                        ++q;
                     }
-                    __syncthreads();                       // queue consumed, s_qn reset: next sweep may append
                 }
             }
             __syncthreads();
+
+            // (d) drain: exact probe of every queued position, four probes in flight per thread
+            {
+                const uint32_t qn = min(s_qn, (uint32_t)kQueueCap);
+                for (uint32_t i0 = (tid & ~31u) * kDrainUnroll; i0 < qn; i0 += kTileThreads * kDrainUnroll) {
+                    // this warp owns entries [i0, i0 + 32 * kDrainUnroll)
+                    uint32_t p[kDrainUnroll];
+                    uint64_t want[kDrainUnroll];
+                    Bucket bk[kDrainUnroll];
+                    uint32_t bucket[kDrainUnroll];
+                    bool on[kDrainUnroll];
+#pragma unroll
+                    for (int u = 0; u < kDrainUnroll; ++u) {
+                        const uint32_t i = i0 + u * 32u + lane;
+                        on[u] = i < qn;
+                        p[u] = on[u] ? s_queue[i] : 0u;
+                        const uint64_t canon = canonical_at(s_packed, p[u], k, kmask);
+                        const uint64_t h = table_hash(canon, k, kmask);
+                        bucket[u] = (uint32_t)(h >> t.rem_bits);
+                        want[u] = (h & t.rem_mask) << 4;
+                        bk[u].s0 = bk[u].s1 = bk[u].s2 = bk[u].s3 = 0ull;
+                        if (on[u]) bk[u] = load_bucket(t.slots + (size_t)bucket[u] * kSlotsPerBucket);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kDrainUnroll; ++u) {
+                        bool found;
+                        uint32_t tag = match_bucket(bk[u], want[u], found);
+                        if (on[u] && !found && (bk[u].s0 & 1ull)) {       // overflowed home bucket
+                            uint32_t bkt = bucket[u];
+                            uint64_t w = want[u];
+                            for (int d = 1; d <= kMaxDisp; ++d) {
+                                bkt = (bkt + 1) & t.bucket_mask;
+                                w += 1;
+                                const Bucket nb = load_bucket(t.slots + (size_t)bkt * kSlotsPerBucket);
+                                ++st_extra;
+                                tag = match_bucket(nb, w, found);
+                                if (found || !(nb.s0 & 1ull)) break;
+                            }
+                        }
+                        if (on[u] && tag) vote(s_votes, s_off, ra, rb, lo + p[u], tag);
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_qn = 0;                        // next append is behind the next pass's barriers
             ra = rb;
         }
 

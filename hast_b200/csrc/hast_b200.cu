@@ -161,10 +161,19 @@ int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv, uint64_t* d_kmers,
     const uint32_t n_tiles = (bv.n_reads + kReadsPerTile - 1) / kReadsPerTile;
     if (!n_tiles) return HAST_OK;
     const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->tile_blocks);
-    if (mode == MODE_CLASSIFY && ctx->opt_kernel == 1)
-        classify_kernel<<<(int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->fused_blocks), kTileThreads, 0, ctx->cs>>>(
-            ctx->tv, bv, ctx->d_counts, (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull), ctx->d_stats);
-    else if (mode == MODE_CLASSIFY)
+    if (mode == MODE_CLASSIFY && ctx->opt_kernel == 1) {
+        const int fgrid = (int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->fused_blocks);
+        const uint32_t nbc = (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull);
+#define HAST_LAUNCH_K(KT) classify_kernel<KT><<<fgrid, kTileThreads, 0, ctx->cs>>>(ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats)
+        switch (ctx->tv.k) {                      // specialised for HAST's default k and the benchmarked sweep
+            case 17: HAST_LAUNCH_K(17); break;
+            case 21: HAST_LAUNCH_K(21); break;
+            case 25: HAST_LAUNCH_K(25); break;
+            case 31: HAST_LAUNCH_K(31); break;
+            default: HAST_LAUNCH_K(0); break;
+        }
+#undef HAST_LAUNCH_K
+    } else if (mode == MODE_CLASSIFY)
         tile_kernel<MODE_CLASSIFY><<<grid, kTileThreads, 0, ctx->cs>>>(
             ctx->tv, bv, ctx->d_counts, (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull),
             ctx->d_stats, nullptr, nullptr);
@@ -221,7 +230,7 @@ int hast_create(int device, hast_ctx** out) {
     int per_sm = 0;
     CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel<MODE_CLASSIFY>, kTileThreads, 0));
     int per_sm_f = 0;
-    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, classify_kernel, kTileThreads, 0));
+    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, classify_kernel<0>, kTileThreads, 0));
 #undef CU_NEW
     ctx->tile_blocks = std::max(1, per_sm) * ctx->sm_count;
     ctx->fused_blocks = std::max(1, per_sm_f) * ctx->sm_count;

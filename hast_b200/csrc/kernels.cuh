@@ -328,8 +328,8 @@ __device__ __forceinline__ void table_insert(const TableView& t, uint64_t canon,
     const uint64_t rem4 = (h & t.rem_mask) << 4;
     const uint64_t tagbits = (uint64_t)(1u << parent) << 1;
     {   // pre-filter first: a key must never be in the table without its filter bits
-        const uint32_t fh = filter_hash(canon);
-        unsigned long long* fw = (unsigned long long*)(t.filt + (fh >> t.filt_shift));
+        const FilterHash fh = filter_hash(canon);
+        unsigned long long* fw = (unsigned long long*)(t.filt + (fh.word >> t.filt_shift));
         const unsigned long long bits = filter_bits(fh);
         if ((*(volatile unsigned long long*)fw & bits) != bits) atomicOr(fw, bits);
     }

@@ -53,17 +53,27 @@ __host__ __device__ __forceinline__ uint64_t table_hash(uint64_t key, int k, uin
     return h;
 }
 
-// 32 well-mixed bits of a canonical k-mer for the pre-filter: top bits pick the
-// word, bits 0-4 / 5-9 pick the bit inside the low / high half of the word
-__host__ __device__ __forceinline__ uint32_t filter_hash(uint64_t canon) {
-    uint32_t m = (uint32_t)canon * 0x9E3779B1u + (uint32_t)(canon >> 32) * 0x85EBCA77u;
+// Pre-filter hash of a canonical k-mer: `word` (32 well-mixed bits, the top ones pick
+// the 64-bit filter word) and `bits` (an independent multiplicative hash whose top
+// 5 + 5 bits pick one bit in the low and one in the high half of that word).  Two
+// separate 32-bit states, so that large filters (> 2^22 words) do not run out of
+// hash entropy.
+struct FilterHash { uint32_t word, bits; };
+__host__ __device__ __forceinline__ FilterHash filter_hash(uint64_t canon) {
+    const uint32_t lo = (uint32_t)canon, hi = (uint32_t)(canon >> 32);
+    uint32_t m = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
     m ^= m >> 15;
     m *= 0xC2B2AE3Du;
     m ^= m >> 13;
-    return m;
+    FilterHash f;
+    f.word = m;
+    f.bits = lo * 0x27D4EB2Fu + hi * 0x165667B1u;
+    return f;
 }
-__host__ __device__ __forceinline__ uint64_t filter_bits(uint32_t h) {
-    return (1ull << (h & 31u)) | (1ull << (32u + ((h >> 5) & 31u)));
+__host__ __device__ __forceinline__ uint32_t filter_bit_lo(FilterHash f) { return f.bits >> 27; }
+__host__ __device__ __forceinline__ uint32_t filter_bit_hi(FilterHash f) { return (f.bits >> 22) & 31u; }
+__host__ __device__ __forceinline__ uint64_t filter_bits(FilterHash f) {
+    return (1ull << filter_bit_lo(f)) | (1ull << (32u + filter_bit_hi(f)));
 }
 
 #ifdef __CUDACC__

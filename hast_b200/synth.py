@@ -366,4 +366,9 @@ def config(name: str) -> TrioSpec:
         return TrioSpec(genome_len=5_000_000, het=0.001, n_pairs=200_000, n_barcodes=10_000)
     if name == "cfg2":       # configs[1]: the single-GPU bench workload
         return TrioSpec(genome_len=100_000_000, het=0.001, n_pairs=20_000_000, n_barcodes=500_000)
+    if name == "cfg3t":      # configs[2] TABLE scale on one GPU: the cfg2 trio and reads, k-mer lists padded with
+        # random decoy k-mers to the ~62 M keys of a human trio, so that the exact table
+        # (1 GiB) is HBM-resident and the pre-filter runs at its size cap
+        return TrioSpec(genome_len=100_000_000, het=0.001, n_pairs=20_000_000, n_barcodes=500_000,
+                        decoy_kmers=26_800_000)
     raise KeyError(name)
