@@ -42,6 +42,18 @@ ALG_BYTES_PER_LOOKUP = 32            # one sector-aligned 4-slot
 SUB_BATCH_READS = 4_000_000          # reads per hast_submit_batch (< 4 GiB of bases each)
 
 
+# stdout carries exactly ONE JSON line.  Libraries underneath (NCCL prints its version to stdout when
+# NCCL_DEBUG is set on the box) write to file descriptor 1, so keep a private copy of the real stdout
+# for the result line and point fd 1 at stderr for everything else.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
+
 def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
@@ -204,7 +216,7 @@ def reference_arm(args):
                        "sample_pairs": sample},
             "cpu_baseline": res,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -431,7 +443,7 @@ def main():
                           "filter_pass_per_step": st["filter_pass"] // args.steps,
                           "filter_pass_frac": st["filter_pass"] / max(1, st["lookups"]),
                           "filter_bytes": int(info.filter_bytes), "kernel": args.kernel}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <unistd.h>
 
 #include "../../include/hast_b200.h"
 #include "fastq_source.h"
@@ -96,6 +97,17 @@ std::string kmer_to_string(uint64_t w, int k) {     // Kmer::ToBaseStr + BaseStr
 
 int run_classify(const Options& opt, RunStats& st) {
     const double t_start = now();
+    // stdout carries the table and nothing else (classify_stlfr_reads.sh:148-149 redirects it into
+    // phased.barcodes).  Libraries underneath (NCCL with NCCL_DEBUG set prints its version to
+    // stdout) must not be able to write into it: keep a private handle for the table and point
+    // file descriptor 1 at stderr for the rest of the process.
+    fflush(stdout);
+    FILE* table_out = nullptr;
+    {
+        const int fd = dup(STDOUT_FILENO);
+        if (fd >= 0) table_out = fdopen(fd, "w");
+        if (!table_out) table_out = stdout; else dup2(STDERR_FILENO, STDOUT_FILENO);
+    }
     // HAST_PARSE_ONLY=1: host front end only (reader, framing, parseName, interning, ordering);
     // prints barcode \t reads \t bases.  A diagnostic for the host logic, it classifies nothing.
     const bool parse_only = getenv("HAST_PARSE_ONLY") != nullptr;
@@ -326,8 +338,9 @@ int run_classify(const Options& opt, RunStats& st) {
         for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
         std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return names[a] < names[b]; });
         for (uint32_t id : order)
-            printf("%s\t%llu\t%llu\n", names[id].c_str(), (unsigned long long)po_tally[2 * (size_t)id],
-                   (unsigned long long)po_tally[2 * (size_t)id + 1]);
+            fprintf(table_out, "%s\t%llu\t%llu\n", names[id].c_str(), (unsigned long long)po_tally[2 * (size_t)id],
+                    (unsigned long long)po_tally[2 * (size_t)id + 1]);
+        fflush(table_out);
         free_batches();
         st.t_total = now() - t_start;
         return 0;
@@ -367,7 +380,8 @@ int run_classify(const Options& opt, RunStats& st) {
     const double t_pr0 = now();
     std::vector<std::string> names;
     index.export_names(names);
-    print_table(stdout, names, counts.data(), st.size0, st.size1, opt.weight0, opt.weight1);
+    print_table(table_out, names, counts.data(), st.size0, st.size1, opt.weight0, opt.weight1);
+    fflush(table_out);
     st.t_print = now() - t_pr0;
     logtime();
     fprintf(stderr, "__END__\n");
