@@ -33,6 +33,11 @@ void print_usage() {
           "B200 build only (long form):\n"
           "        --gpus N                        GPUs of this box to use (default: all visible; env HAST_GPUS).\n"
           "        --stats-json FILE               write throughput statistics as JSON.\n"
+          "        --split-barcodes                also write {paternal,maternal,homozygous}.unique.barcodes\n"
+          "                                        (the three awk passes of classify_stlfr_reads.sh).\n"
+          "        --partition-reads               also write NAME.{paternal,maternal,homozygous,nobarcode}.fastq\n"
+          "                                        and filter_reads.log for every --read (quartering_fastq.awk).\n"
+          "        --outdir DIR                    where those extra files go (default: current directory).\n"
           "\n"
           "Examples:\n"
           "    ./classify --hap0 p.kmers --hap1 m.kmers --read input.fastq.gz\n"
@@ -53,7 +58,9 @@ int parse_options(int argc, char** argv, Options& opt) {
         {"weight0", required_argument, nullptr, 'w'},   {"weight1", required_argument, nullptr, 'u'},
         {"adaptor_f", required_argument, nullptr, 'f'}, {"adaptor_r", required_argument, nullptr, 'q'},
         {"help", no_argument, nullptr, 'h'},            {"gpus", required_argument, nullptr, 1000},
-        {"stats-json", required_argument, nullptr, 1001}, {nullptr, 0, nullptr, 0}};
+        {"stats-json", required_argument, nullptr, 1001}, {"split-barcodes", no_argument, nullptr, 1002},
+        {"partition-reads", no_argument, nullptr, 1003}, {"outdir", required_argument, nullptr, 1004},
+        {nullptr, 0, nullptr, 0}};
     // classify.cpp:387 -- includes the dead "l:" so that "-l x" falls to the usage branch
     static const char optstring[] = "p:m:l:r:t:w:u:f:q:h";
     if (const char* e = getenv("HAST_GPUS")) opt.gpus = atoi(e);
@@ -74,6 +81,9 @@ int parse_options(int argc, char** argv, Options& opt) {
             case 'w': opt.weight0 = atof(optarg); break;       // :417
             case 1000: opt.gpus = atoi(optarg); break;
             case 1001: opt.stats_json = optarg; break;
+            case 1002: opt.split_barcodes = true; break;
+            case 1003: opt.partition_reads = opt.split_barcodes = true; break;
+            case 1004: opt.outdir = optarg; break;
             case 'h':
             default:
                 print_usage();

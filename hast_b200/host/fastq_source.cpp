@@ -30,7 +30,10 @@ std::string FastqSource::open(const std::string& path) {
     path_ = path;
     const size_t n = path.size();
     const bool gz = n > 3 && path[n - 3] == '.' && path[n - 2] == 'g' && path[n - 1] == 'z';   // classify.cpp:245-250
-    if (gz) {
+    if (path == "-") {                                 // standard input (plain text), as `awk ... -`
+        fd_ = dup(STDIN_FILENO);
+        if (fd_ < 0) return std::string("cannot read standard input: ") + strerror(errno);
+    } else if (gz) {
         gz_ = gzopen(path.c_str(), "rb");
         if (!gz_) return "cannot open " + path;
         gzbuffer(gz_, 1u << 20);

@@ -46,7 +46,7 @@ static inline char* put_int(char* p, long v) {
 // (bytewise lexicographic, e.g. "0_0_0" < "10_1_1" < "1_2_3"), one line
 // barcode \t hap \t count0 \t count1.
 void print_table(FILE* out, const std::vector<std::string>& names, const int32_t* counts, uint64_t n0,
-                 uint64_t n1, double w0, double w1) {
+                 uint64_t n1, double w0, double w1, std::vector<uint32_t>* order_out, std::vector<int8_t>* hap_out) {
     std::vector<uint32_t> order(names.size());
     std::iota(order.begin(), order.end(), 0u);
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return names[a] < names[b]; });
@@ -63,7 +63,9 @@ void print_table(FILE* out, const std::vector<std::string>& names, const int32_t
         memcpy(buf.data() + len, nm.data(), nm.size());
         char* p = buf.data() + len + nm.size();
         *p++ = '\t';
-        p = put_int(p, get_hap(nm, c0, c1, n0, n1, w0, w1));
+        const int hap = get_hap(nm, c0, c1, n0, n1, w0, w1);
+        if (hap_out) hap_out->push_back((int8_t)hap);
+        p = put_int(p, hap);
         *p++ = '\t';
         p = put_int(p, c0);
         *p++ = '\t';
@@ -73,6 +75,7 @@ void print_table(FILE* out, const std::vector<std::string>& names, const int32_t
     }
     fwrite(buf.data(), 1, len, out);
     fflush(out);
+    if (order_out) order_out->swap(order);
 }
 
 }  // namespace hasthost

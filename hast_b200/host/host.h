@@ -26,6 +26,9 @@ struct Options {
     // extensions (long options only; the reference rejects them, so no clash)
     int gpus = 0;                          // 0 = all visible
     std::string stats_json;                // throughput side output
+    bool split_barcodes = false;           // also write the three *.unique.barcodes lists (script :156-162)
+    bool partition_reads = false;          // also partition every input FASTQ (script :176-185); implies split
+    std::string outdir;                    // where those files go ("" = cwd, like the script)
     size_t batch_bytes = 32u << 20;        // raw FASTQ text per parse block
 };
 // returns 0 to run, otherwise the process exit code (255 after printing usage)
@@ -97,8 +100,44 @@ bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out);
 
 // ---- haplotype call + table output (classify.cpp:66-102) ----------------------
 int get_hap(const std::string& barcode, int c0, int c1, uint64_t n0, uint64_t n1, double w0, double w1);
+// order_out / hap_out (optional): the barcode ids in output order and their calls
 void print_table(FILE* out, const std::vector<std::string>& names, const int32_t* counts, uint64_t n0,
-                 uint64_t n1, double w0, double w1);
+                 uint64_t n1, double w0, double w1, std::vector<uint32_t>* order_out = nullptr,
+                 std::vector<int8_t>* hap_out = nullptr);
+
+// ---- stage-01 post-processing (classify_stlfr_reads.sh:156-185, quartering_fastq.awk) ----
+// The three awk associative arrays of quartering_fastq.awk:12-18 as one table.
+class BarcodeLists {
+public:
+    enum { kPaternal = 1, kMaternal = 2, kHomozygous = 3 };
+    // one list line (no '\n'); the key is its $1 under FS '#|/'
+    void add(const char* line, size_t n, int type);
+    std::string load(const std::string& path, int type);      // "" or an error message
+    int find(const char* key, size_t n) const;                // 0 = in no list
+    size_t size() const { return count_; }
+private:
+    static constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+    struct Slot { uint64_t hash = 0; uint64_t off = 0; uint32_t len = kEmpty; uint8_t types = 0; };
+    void grow();
+    std::vector<Slot> slots_;
+    std::vector<char> arena_;
+    size_t count_ = 0;
+};
+struct PartitionStats {
+    uint64_t total = 0, no_barcode = 0, paternal = 0, maternal = 0, homozygous = 0, unclassified = 0;
+    uint64_t text_bytes = 0;
+};
+// {paternal,maternal,homozygous}.unique.barcodes from the table rows (barcode, call, counts) in
+// output order, with the awk field rules of classify_stlfr_reads.sh:157,160,163; lists (optional)
+// receives exactly the lines written.  counts_out = lines per file.
+std::string write_barcode_lists(const std::string& dir, const std::vector<std::string>& names,
+                                const std::vector<uint32_t>& order, const std::vector<int8_t>& haps,
+                                const int32_t* counts, uint64_t counts_out[3], BarcodeLists* lists);
+// quartering_fastq.awk over one FASTQ(.gz | "-"): PREFIX.{paternal,maternal,homozygous,nobarcode}.fastq
+// and filter_reads.log (appended) in outdir ("" = cwd).  display_name is awk's FILENAME.
+std::string partition_fastq(const std::string& input, const std::string& display_name, const std::string& prefix,
+                            const std::string& outdir, const BarcodeLists& lists, PartitionStats& st);
+std::string partition_prefix(const std::string& path);       // basename, ".gz" stripped (:178-180)
 
 // ---- the pipeline ---------------------------------------------------------------
 struct RunStats {
@@ -106,6 +145,8 @@ struct RunStats {
     double t_table = 0, t_reads = 0, t_finish = 0, t_print = 0, t_total = 0;
     int gpus = 0, parser_threads = 0;
     uint64_t table_bytes = 0, size0 = 0, size1 = 0, kernel_launches = 0;
+    double t_split = 0, t_partition = 0;
+    uint64_t partition_text_bytes = 0;
 };
 int run_classify(const Options& opt, RunStats& st);
 

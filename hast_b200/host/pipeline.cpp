@@ -380,13 +380,45 @@ int run_classify(const Options& opt, RunStats& st) {
     const double t_pr0 = now();
     std::vector<std::string> names;
     index.export_names(names);
-    print_table(table_out, names, counts.data(), st.size0, st.size1, opt.weight0, opt.weight1);
+    std::vector<uint32_t> order;
+    std::vector<int8_t> haps;
+    print_table(table_out, names, counts.data(), st.size0, st.size1, opt.weight0, opt.weight1,
+                opt.split_barcodes ? &order : nullptr, opt.split_barcodes ? &haps : nullptr);
     fflush(table_out);
     st.t_print = now() - t_pr0;
     logtime();
-    fprintf(stderr, "__END__\n");
     free_batches();
     cleanup();
+
+    // ---- optional: the rest of classify_stlfr_reads.sh (:156-185) in the same process ----
+    if (opt.split_barcodes) {
+        const double t0 = now();
+        BarcodeLists lists;
+        uint64_t n3[3];
+        const std::string e = write_barcode_lists(opt.outdir, names, order, haps, counts.data(), n3,
+                                                  opt.partition_reads ? &lists : nullptr);
+        if (!e.empty()) { fprintf(stderr, "ERROR : %s\n", e.c_str()); return 1; }
+        fprintf(stderr, "final paternal barcode : %llu\nfinal maternal barcodes : %llu\nfinal homozygous barcodes : %llu\n",
+                (unsigned long long)n3[0], (unsigned long long)n3[1], (unsigned long long)n3[2]);
+        st.t_split = now() - t0;
+        if (opt.partition_reads) {
+            const double t1 = now();
+            fprintf(stderr, "phase reads ...\n");
+            for (const std::string& path : opt.reads) {
+                const bool gz = path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
+                PartitionStats ps;
+                // the script pipes gzip input into `awk ... -`, whose FILENAME is then "-" (:181)
+                const std::string e2 = partition_fastq(path, gz ? "-" : path, partition_prefix(path), opt.outdir,
+                                                       lists, ps);
+                if (!e2.empty()) { fprintf(stderr, "ERROR : %s\n", e2.c_str()); return 1; }
+                st.partition_text_bytes += ps.text_bytes;
+            }
+            st.t_partition = now() - t1;
+            fprintf(stderr, "phase reads done\n");
+            logtime();
+        }
+    }
+    fprintf(stderr, "__END__\n");
     st.t_total = now() - t_start;
     return 0;
 }

@@ -115,3 +115,44 @@ def test_cli_then_stage_script_awk_split(trio_files, tmp_path):
         out = subprocess.run(["awk", f"{cond}{{print $1}}", str(tmp_path / "phased.barcodes")], capture_output=True)
         n[name] = len(out.stdout.splitlines())
     assert sum(n.values()) == len(r.stdout.splitlines()) and n["paternal"] > 0 and n["maternal"] > 0
+
+
+def test_cli_split_and_partition_equal_the_script_flow(trio_files, tmp_path):
+    """bin/classify --partition-reads does classify_stlfr_reads.sh:148-185 in one process: the table on
+    stdout, the three barcode lists (:156-162) and quartering_fastq.awk's outputs (:176-185) for every
+    input, identical to running the awk programs (restated in oracle/stage01_post.py) on the table."""
+    import sys
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import stage01_post as post
+    t, d, pat, mat, plain, gz = trio_files
+    out = tmp_path / "out"
+    out.mkdir()
+    reads = [plain[0], gz[1]]                          # one plain, one gzip input
+    r = run_cli(["--hap0", pat, "--hap1", mat, "--read", reads[0], "--read", reads[1], "--weight0", "1.04",
+                 "--partition-reads", "--outdir", out])
+    assert r.returncode == 0, r.stderr[-600:].decode(errors="replace")
+    table = r.stdout
+    want_lists = post.split_barcodes(table)
+    names = ["paternal.unique.barcodes", "maternal.unique.barcodes", "homozygous.unique.barcodes"]
+    for nm, want in zip(names, want_lists):
+        assert (out / nm).read_bytes() == want
+    assert all(len(w) > 0 for w in want_lists)
+    log = b""
+    import gzip as gz_mod
+    for path in reads:
+        raw = Path(path).read_bytes()
+        is_gz = str(path).endswith(".gz")
+        text = gz_mod.decompress(raw) if is_gz else raw
+        prefix = Path(path).name[:-3] if is_gz else Path(path).name
+        files, lg, _ = post.quartering(*want_lists, text, b"-" if is_gz else str(path).encode())
+        log += lg
+        for suffix in ("nobarcode", "paternal", "maternal", "homozygous"):
+            p = out / f"{prefix}.{suffix}.fastq"
+            assert (p.read_bytes() if p.exists() else None) == files.get(suffix), (prefix, suffix)
+        assert sum(len(v) for v in files.values()) == len(text)      # every record lands somewhere
+    assert (out / "filter_reads.log").read_bytes() == log
+    # --split-barcodes alone writes the lists and no FASTQ
+    out2 = tmp_path / "out2"
+    out2.mkdir()
+    r = run_cli(["--hap0", pat, "--hap1", mat, "--read", reads[0], "--weight0", "1.04", "--split-barcodes", "--outdir", out2])
+    assert r.returncode == 0 and sorted(p.name for p in out2.iterdir()) == sorted(names)
