@@ -241,7 +241,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--table-scale", type=float, default=1.0, help="expected_keys multiplier (sparser table)")
-    ap.add_argument("--kernel", type=int, default=1, choices=[0, 1],
+    ap.add_argument("--kernel", type=int, default=1, choices=[0, 1, 2],
                     help="1 = pre-filtered fused kernel (default), 0 = direct table probe per position")
     ap.add_argument("--filter-bits", type=int, default=16, help="pre-filter bits per key")
     ap.add_argument("--filter-max-mib", type=int, default=64, help="pre-filter size cap (MiB)")
@@ -372,7 +372,7 @@ def main():
     gather = eng.gather_roofline(1 << 28, 4 << 30) if rank == 0 else None
     gather_tbl = eng.gather_roofline(1 << 28, info.bytes) if rank == 0 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "classify_kernel" if args.kernel == 1 else "tile_kernel<MODE_CLASSIFY>", "launches_per_step": len(batches),
+                "traffic": traffic, "kernel": "classify_kernel" if args.kernel >= 1 else "tile_kernel<MODE_CLASSIFY>", "launches_per_step": len(batches),
                 "ms_per_launch": ms_kernel / len(batches),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                 "lookups_per_s": lookups_step / (ms_kernel * 1e-3),

@@ -92,7 +92,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    p = Path(path) if path else Path(os.environ.get("HAST_B200_LIB", LIB_PATH))   # env: A/B builds of the library
     if not p.exists():
         raise FileNotFoundError(
             f"{p} not found: build it with `make lib` (or __graft_entry__.build()); "

@@ -35,9 +35,46 @@
 
 namespace hast {
 
+// Two ways of getting a pass's read bytes on chip (template parameter TMA):
+//   false  every thread issues 128-bit streaming loads (L2 evict-first) and packs them straight
+//          into shared memory -- no staging buffer;
+//   true   one thread streams the NEXT pass into a raw staging buffer with a TMA bulk copy
+//          (cp.async.bulk + mbarrier) while the current pass is swept; packing then reads shared memory.
+// Measured on B200 (cfg2, G lookups/s): direct 218; TMA with a 8 / 16 / 24 / 32 KiB staging buffer
+// 172 / 199 / 205 / 142.  The staging buffer costs what this kernel needs most: L1.  The random filter
+// probes in flight (~0.75 sectors/clk/SM x ~800 clk) each hold a 128-byte L1 line until they return,
+// and shared memory is carved out of the same 256 KiB array, so a CTA footprint beyond ~45 KiB (x4)
+// throttles the sweep, while a small buffer means more passes and their fixed cost.  The direct
+// path is the default; the TMA path stays selectable (hast_set_option "kernel" = 2).
+#ifndef HAST_PASS_CAP_TMA
+#define HAST_PASS_CAP_TMA 24576
+#endif
+#ifndef HAST_PASS_CAP
+#define HAST_PASS_CAP 40960
+#endif
+#ifndef HAST_READS_PER_TILE
+#define HAST_READS_PER_TILE 240
+#endif
+constexpr int kFusedReadsPerTile = HAST_READS_PER_TILE;
 constexpr int kQueueCap = 6144;                          // passing positions buffered per CTA
 constexpr int kChunk = 16;                               // positions per thread per sweep (= bases per packed word)
 constexpr int kDrainUnroll = 4;                          // exact probes in flight per thread while draining
+
+template <bool TMA>
+struct __align__(128) FusedSmem {
+    static constexpr int kCap = TMA ? HAST_PASS_CAP_TMA : HAST_PASS_CAP;   // read bytes per pass (longest read: cap - 16)
+    static constexpr int kWords = kCap / 16;             // packed words (16 bases each)
+    uint8_t raw[TMA ? kCap : 16];                        // TMA destination: the pass's ASCII bytes
+    uint32_t packed[kWords + 4];                         // 2-bit MSB-first, 16 bases per word
+    uint32_t bad[kWords / 2 + 2];                        // 1 bit per position: starts no k-mer
+    uint16_t queue[kQueueCap];                           // positions that passed the pre-filter
+    uint32_t off[kFusedReadsPerTile + 1];
+    uint32_t votes[kFusedReadsPerTile];
+    unsigned long long mbar;                             // completion barrier of the bulk copy into raw
+    uint32_t qn;
+};
+static_assert(4 * (sizeof(FusedSmem<true>) + 1024) <= 227 * 1024, "four CTAs per SM must fit");
+static_assert(4 * (sizeof(FusedSmem<false>) + 1024) <= 227 * 1024, "four CTAs per SM must fit");
 
 // hit at global base offset gp: add the tag bits to the vote word of the read that owns it,
 // s_off[r] <= gp < s_off[r+1] with r in [ra, rb)
@@ -63,6 +100,7 @@ __device__ __forceinline__ uint64_t load_filter(const uint64_t* p, uint64_t pol)
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
     return v;
 }
+
 // 16 read bytes, used once: do not let them push the filter / table out of L2
 __device__ __forceinline__ uint4 load_stream16_ef(const uint8_t* p, uint64_t pol) {
     uint4 v;
@@ -71,17 +109,52 @@ __device__ __forceinline__ uint4 load_stream16_ef(const uint8_t* p, uint64_t pol
     return v;
 }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// One thread: stream `bytes` (multiple of 16, > 0) from global into shared memory, evict-first in
+// L2 (read once: must not push the filter / table out), completion signalled on `bar`.
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar,
+                                            uint64_t policy) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 // KT > 0: k is the compile-time constant KT (shift amounts fold into immediates); KT == 0: any k in 1..32.
-template <int KT>
+template <int KT, bool TMA>
 __global__ void __launch_bounds__(kTileThreads, 4)
 classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_barcodes,
                 DevStats* __restrict__ stats) {
-    __shared__ uint32_t s_off[kReadsPerTile + 1];
-    __shared__ uint32_t s_votes[kReadsPerTile];
-    __shared__ uint32_t s_packed[kTileWords + 4];
-    __shared__ uint32_t s_bad[kTileWords / 2 + 2];
-    __shared__ uint16_t s_queue[kQueueCap];
-    __shared__ uint32_t s_qn;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    using Smem = FusedSmem<TMA>;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    constexpr uint32_t kPassCapBytes = Smem::kCap;
+    constexpr uint32_t kReadsPerTile = kFusedReadsPerTile;
+    uint32_t* const s_off = sm.off;
+    uint32_t* const s_votes = sm.votes;
+    uint32_t* const s_packed = sm.packed;
+    uint32_t* const s_bad = sm.bad;
+    uint16_t* const s_queue = sm.queue;
+    uint32_t& s_qn = sm.qn;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const int k = KT ? KT : t.k;
@@ -100,13 +173,39 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
     unsigned long long st_lookups = 0, st_n = 0, st_short = 0, st_long = 0, st_badbc = 0;
     uint32_t st_extra = 0, st_pass = 0;
 
+    // The read bytes of pass i+1 are streamed into sm.raw by one bulk copy while pass i is being
+    // swept (raw is only needed until pass i has been packed).  Thread 0 issues, everybody waits
+    // on the mbarrier; exactly one copy (or a bare arrive for an empty range) per pass, in order.
+    auto prefetch = [&](uint32_t lo16, uint32_t end) {           // thread 0 only; bytes [lo16, end) of the batch
+        if (!TMA) return;
+        const uint32_t bytes = min((uint32_t)kPassCapBytes, (end - lo16 + 15u) & ~15u);
+        if (bytes) tma_load_1d(sm.raw, b.bases + lo16, bytes, &sm.mbar, pol_first);
+        else mbar_arrive(&sm.mbar);
+    };
+    uint32_t parity = 0;
     if (tid == 0) s_qn = 0;
+    if (TMA && tid == 0) {
+        mbar_init(&sm.mbar, 1);
+        const uint32_t r0 = blockIdx.x * kReadsPerTile;           // grid <= n_tiles: the first tile exists
+        const uint32_t R = min((uint32_t)kReadsPerTile, b.n_reads - r0);
+        prefetch(b.read_off[r0] & ~15u, b.read_off[r0 + R]);
+    }
+    __syncthreads();
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t r0 = tile * kReadsPerTile;
         const uint32_t R = min((uint32_t)kReadsPerTile, b.n_reads - r0);
         for (uint32_t i = tid; i <= R; i += kTileThreads) s_off[i] = b.read_off[r0 + i];
         for (uint32_t i = tid; i < R; i += kTileThreads) s_votes[i] = 0;
+        // first pass of this CTA's next tile (thread 0 keeps its byte range in registers)
+        const uint32_t ntile = tile + gridDim.x;
+        uint32_t nt_lo = 0, nt_end = 0;
+        if (TMA && tid == 0 && ntile < n_tiles) {
+            const uint32_t nr0 = ntile * kReadsPerTile;
+            const uint32_t nR = min((uint32_t)kReadsPerTile, b.n_reads - nr0);
+            nt_lo = b.read_off[nr0] & ~15u;
+            nt_end = b.read_off[nr0 + nR];
+        }
         __syncthreads();
 
         uint32_t ra = 0;
@@ -118,34 +217,39 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                 uint32_t a = ra, c = R;                    // largest rb with s_off[rb] - lo <= cap
                 while (a < c) {
                     const uint32_t m = (a + c + 1) >> 1;
-                    if (s_off[m] - lo <= (uint32_t)kTileCapBytes) a = m; else c = m - 1;
+                    if (s_off[m] - lo <= (uint32_t)kPassCapBytes) a = m; else c = m - 1;
                 }
                 rb = a;
             }
-            if (rb == ra) {                                // a single read larger than a pass
-                if (tid == 0) ++st_long;
-                ra += 1;
-                continue;
-            }
-            const uint32_t hi = s_off[rb];
+            const bool too_long = rb == ra;                // a single read larger than a pass: skipped, reported
+            if (too_long) rb = ra + 1;
+            const uint32_t hi = too_long ? lo : s_off[rb];
             const uint32_t nseg = (hi - lo + 15u) >> 4;
 
             for (uint32_t i = tid; i < (nseg >> 1) + 2; i += kTileThreads) s_bad[i] = 0;
+            if (TMA) {
+                mbar_wait(&sm.mbar, parity);               // this pass's bytes have landed in sm.raw
+                parity ^= 1u;
+            }
             __syncthreads();
 
-            // (a) pack
+            // (a) pack: 16 ASCII bytes -> one 2-bit word; 'N' bytes flagged
             for (uint32_t seg = tid; seg < nseg + 4; seg += kTileThreads) {
                 uint32_t word = 0;
                 if (seg < nseg) {
-                    const uint64_t g = (uint64_t)lo + 16ull * seg;
                     uint4 v;
-                    if (g + 16 <= b.n_bases) {
-                        v = load_stream16_ef(b.bases + g, pol_first);
-                    } else {                               // last, partial segment of the batch
-                        uint32_t w[4] = {0, 0, 0, 0};
-                        for (uint32_t j = 0; j < 16 && g + j < b.n_bases; ++j)
-                            w[j >> 2] |= (uint32_t)b.bases[g + j] << (8 * (j & 3));
-                        v = make_uint4(w[0], w[1], w[2], w[3]);
+                    if (TMA) {
+                        v = *reinterpret_cast<const uint4*>(sm.raw + 16u * seg);
+                    } else {
+                        const uint64_t g = (uint64_t)lo + 16ull * seg;
+                        if (g + 16 <= b.n_bases) {
+                            v = load_stream16_ef(b.bases + g, pol_first);
+                        } else {                           // last, partial segment of the batch
+                            uint32_t w[4] = {0, 0, 0, 0};
+                            for (uint32_t j = 0; j < 16 && g + j < b.n_bases; ++j)
+                                w[j >> 2] |= (uint32_t)b.bases[g + j] << (8 * (j & 3));
+                            v = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
                     }
                     word = pack16(v);
                     if (any_N4(v.x) | any_N4(v.y) | any_N4(v.z) | any_N4(v.w)) {
@@ -159,6 +263,16 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                 s_packed[seg] = word;
             }
             __syncthreads();
+            // sm.raw is free again: stream in the next pass (of this tile, else of the next tile)
+            if (TMA && tid == 0) {
+                if (rb < R) prefetch(s_off[rb] & ~15u, s_off[R]);
+                else if (ntile < n_tiles) prefetch(nt_lo, nt_end);
+            }
+            if (too_long) {
+                if (tid == 0) ++st_long;
+                ra = rb;
+                continue;
+            }
 
             // (b) per read: containN (classify.cpp:182-185), positions that start no k-mer
             for (uint32_t r = ra + tid; r < rb; r += kTileThreads) {

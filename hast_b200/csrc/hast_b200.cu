@@ -106,10 +106,10 @@ struct hast_ctx {
     int nranks = 1, rank = 0;
 
     int tile_blocks = 0;                  // persistent grid of the tile kernels
-    int fused_blocks = 0;                 // persistent grid of classify_kernel
+    int fused_blocks = 0, fused_blocks_tma = 0;   // persistent grids of classify_kernel<*, false / true>
     uint64_t filt_words = 0;
     // options (hast_set_option)
-    int64_t opt_kernel = 1;               // 1 = classify_kernel (pre-filter), 0 = tile_kernel<MODE_CLASSIFY> (direct probe)
+    int64_t opt_kernel = 1;               // 1 = classify_kernel (pre-filter), 2 = same with TMA-staged reads, 0 = tile_kernel<MODE_CLASSIFY>
     int64_t opt_filter_bits_per_key = 16;
     int64_t opt_filter_max_bytes = (int64_t)64 << 20;
     std::string err;
@@ -161,10 +161,18 @@ int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv, uint64_t* d_kmers,
     const uint32_t n_tiles = (bv.n_reads + kReadsPerTile - 1) / kReadsPerTile;
     if (!n_tiles) return HAST_OK;
     const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->tile_blocks);
-    if (mode == MODE_CLASSIFY && ctx->opt_kernel == 1) {
-        const int fgrid = (int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->fused_blocks);
+    if (mode == MODE_CLASSIFY && ctx->opt_kernel >= 1) {
+        const uint32_t n_ftiles = (bv.n_reads + kFusedReadsPerTile - 1) / kFusedReadsPerTile;
+        const bool tma = ctx->opt_kernel == 2;
+        const int fgrid = (int)std::min<uint32_t>(n_ftiles, (uint32_t)(tma ? ctx->fused_blocks_tma : ctx->fused_blocks));
         const uint32_t nbc = (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull);
-#define HAST_LAUNCH_K(KT) classify_kernel<KT><<<fgrid, kTileThreads, 0, ctx->cs>>>(ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats)
+#define HAST_LAUNCH_K(KT)                                                                                         \
+    do {                                                                                                          \
+        if (tma) classify_kernel<KT, true><<<fgrid, kTileThreads, sizeof(FusedSmem<true>), ctx->cs>>>(            \
+                ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                                   \
+        else classify_kernel<KT, false><<<fgrid, kTileThreads, sizeof(FusedSmem<false>), ctx->cs>>>(              \
+                ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                                   \
+    } while (0)
         switch (ctx->tv.k) {                      // specialised for HAST's default k and the benchmarked sweep
             case 17: HAST_LAUNCH_K(17); break;
             case 21: HAST_LAUNCH_K(21); break;
@@ -229,8 +237,20 @@ int hast_create(int device, hast_ctx** out) {
     CU_NEW(cudaMemset(ctx->d_stats, 0, sizeof(DevStats)));
     int per_sm = 0;
     CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel<MODE_CLASSIFY>, kTileThreads, 0));
-    int per_sm_f = 0;
-    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, classify_kernel<0>, kTileThreads, 0));
+    // classify_kernel keeps its pass in dynamic shared memory (opt-in above 48 KiB for the TMA variant)
+#define HAST_ATTR(KT)                                                                                              \
+    CU_NEW(cudaFuncSetAttribute(classify_kernel<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                (int)sizeof(FusedSmem<false>)));                                                   \
+    CU_NEW(cudaFuncSetAttribute(classify_kernel<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                (int)sizeof(FusedSmem<true>)));
+    HAST_ATTR(0) HAST_ATTR(17) HAST_ATTR(21) HAST_ATTR(25) HAST_ATTR(31)
+#undef HAST_ATTR
+    int per_sm_f = 0, per_sm_t = 0;
+    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, classify_kernel<0, false>, kTileThreads,
+                                                         sizeof(FusedSmem<false>)));
+    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, classify_kernel<0, true>, kTileThreads,
+                                                         sizeof(FusedSmem<true>)));
+    ctx->fused_blocks_tma = std::max(1, per_sm_t) * prop.multiProcessorCount;
 #undef CU_NEW
     ctx->tile_blocks = std::max(1, per_sm) * ctx->sm_count;
     ctx->fused_blocks = std::max(1, per_sm_f) * ctx->sm_count;
@@ -265,7 +285,8 @@ int hast_set_option(hast_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return fail(ctx, HAST_E_ARG, "NULL argument");
     const std::string n(name);
     if (n == "kernel") {
-        if (value != 0 && value != 1) return fail(ctx, HAST_E_ARG, "kernel: 0 (direct probe) or 1 (pre-filter)");
+        if (value < 0 || value > 2)
+            return fail(ctx, HAST_E_ARG, "kernel: 0 (direct probe), 1 (pre-filter), 2 (pre-filter, TMA-staged reads)");
         ctx->opt_kernel = value;
     } else if (n == "filter_bits_per_key") {
         if (value < 1 || value > 64) return fail(ctx, HAST_E_ARG, "filter_bits_per_key: 1..64");
@@ -625,7 +646,7 @@ int hast_finish(hast_ctx* ctx, int32_t* counts_out, uint64_t n_barcodes) {
                     std::to_string(ctx->tv.k) + " (the reference aborts on these, kmer.h:171)");
     if (ds.reads_too_long)
         return fail(ctx, HAST_E_ARG, std::to_string(ds.reads_too_long) + " read(s) longer than " +
-                    std::to_string(kTileCapBytes - 16) + " bases");
+                    std::to_string((ctx->opt_kernel == 2 ? FusedSmem<true>::kCap : ctx->opt_kernel == 1 ? FusedSmem<false>::kCap : kTileCapBytes) - 16) + " bases");
     if (ds.bad_barcode)
         return fail(ctx, HAST_E_ARG, std::to_string(ds.bad_barcode) + " read(s) with barcode id >= reserved barcodes");
     if (n_barcodes > ctx->n_barcodes) return fail(ctx, HAST_E_ARG, "n_barcodes exceeds reserved barcodes");

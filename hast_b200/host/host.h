@@ -29,7 +29,7 @@ struct Options {
     bool split_barcodes = false;           // also write the three *.unique.barcodes lists (script :156-162)
     bool partition_reads = false;          // also partition every input FASTQ (script :176-185); implies split
     std::string outdir;                    // where those files go ("" = cwd, like the script)
-    size_t batch_bytes = 32u << 20;        // raw FASTQ text per parse block
+    size_t batch_bytes = 8u << 20;         // raw FASTQ text per parse block
 };
 // returns 0 to run, otherwise the process exit code (255 after printing usage)
 int parse_options(int argc, char** argv, Options& opt);

@@ -196,9 +196,9 @@ int run_classify(const Options& opt, RunStats& st) {
     const size_t n_batches = (size_t)opt.threads + 3 * (size_t)n_gpu + 1;
     Shared sh;
     BarcodeIndex index;
-    Queue<TextBlock*> q_text((size_t)opt.threads + 2), q_text_free(1u << 20);
+    Queue<TextBlock*> q_text((size_t)opt.threads + 8 + 2), q_text_free(1u << 20);
     Queue<Batch*> q_batch(n_batches), q_batch_free(1u << 20);
-    std::vector<TextBlock> text_pool((size_t)opt.threads + 3);
+    std::vector<TextBlock> text_pool((size_t)opt.threads + 8 + 3);
     std::vector<Batch> batch_pool(n_batches);
     for (auto& t : text_pool) q_text_free.push(&t);
     bool alloc_ok = true;
@@ -229,26 +229,40 @@ int run_classify(const Options& opt, RunStats& st) {
     }
     auto abort_all = [&] { q_text.abort(); q_text_free.abort(); q_batch.abort(); q_batch_free.abort(); };
 
+    // Readers: one thread per input file, several files at once.  Inflating a gzip stream is serial
+    // and by far the slowest stage of the whole program (~0.2-0.4 GB/s of text per core against
+    // > 100 GB/s the GPUs classify), but the files of a run (r1/r2, lanes) are independent and the
+    // per-barcode sums do not depend on the order in which reads arrive.
     std::atomic<uint64_t> text_bytes{0};
-    std::thread reader([&] {
-        for (const std::string& path : opt.reads) {
-            fprintf(stderr, "__process read: %s\n", path.c_str());
-            FastqSource src;
-            std::string e = src.open(path);
-            if (!e.empty()) { sh.fail(e); abort_all(); return; }
+    std::atomic<size_t> next_file{0};
+    const int n_readers = (int)std::max<size_t>(1, std::min<size_t>({opt.reads.size(), (size_t)opt.threads, (size_t)8}));
+    std::atomic<int> readers_left{n_readers};
+    std::vector<std::thread> readers;
+    for (int r = 0; r < n_readers; ++r)
+        readers.emplace_back([&] {
             for (;;) {
-                TextBlock* blk = nullptr;
-                if (!q_text_free.pop(blk)) return;
-                std::string err;
-                const bool more = src.next(*blk, block_bytes - 8192, err);
-                if (!err.empty()) { sh.fail(err); abort_all(); return; }
-                if (!more) { q_text_free.push(blk); break; }
-                if (!q_text.push(blk)) return;
+                const size_t fi = next_file.fetch_add(1);
+                if (fi >= opt.reads.size() || sh.failed) break;
+                const std::string& path = opt.reads[fi];
+                fprintf(stderr, "__process read: %s\n", path.c_str());
+                FastqSource src;
+                std::string e = src.open(path);
+                if (!e.empty()) { sh.fail(e); abort_all(); break; }
+                bool stop = false;
+                for (;;) {
+                    TextBlock* blk = nullptr;
+                    if (!q_text_free.pop(blk)) { stop = true; break; }
+                    std::string err;
+                    const bool more = src.next(*blk, block_bytes - 8192, err);
+                    if (!err.empty()) { sh.fail(err); abort_all(); stop = true; break; }
+                    if (!more) { q_text_free.push(blk); break; }
+                    if (!q_text.push(blk)) { stop = true; break; }
+                }
+                text_bytes += src.bytes_out();
+                if (stop) break;
             }
-            text_bytes += src.bytes_out();
-        }
-        q_text.finish();
-    });
+            if (--readers_left == 0) q_text.finish();
+        });
 
     std::atomic<int> parsers_left{opt.threads};
     std::vector<std::thread> parsers;
@@ -315,7 +329,7 @@ int run_classify(const Options& opt, RunStats& st) {
             for (auto& f : inflight) q_batch_free.push(f.second);
         });
 
-    reader.join();
+    for (auto& t : readers) t.join();
     for (auto& t : parsers) t.join();
     for (auto& t : gpu_threads) t.join();
     if (sh.failed) {

@@ -44,9 +44,9 @@ def _built():
     yield
 
 
-@pytest.fixture(scope="session", params=[1, 0], ids=["prefilter", "direct"])
+@pytest.fixture(scope="session", params=[1, 0, 2], ids=["prefilter", "direct", "prefilter_tma"])
 def engine(request):
-    """One context per fused-kernel variant: 1 = Bloom pre-filter + exact table (default),
+    """One context per fused-kernel variant: 1 = Bloom pre-filter + exact table (default), 2 = the same with TMA-staged read bytes,
     0 = direct table probe per position.  Both must be bit-identical to the oracle."""
     from hast_b200.capi import Engine
     e = Engine(0)
