@@ -416,6 +416,60 @@ def main():
                "path": "hast_submit_batch (pinned host buffers, double-buffered cudaMemcpyAsync) + hast_finish"}
         del h_bases
 
+        # ---- the same step with batches as the C++ parser hands them over by default: 2-bit packed ----
+        if args.kernel >= 1:
+            shifts = (30 - 2 * torch.arange(16, device=dev, dtype=torch.int64))
+            pk_w, pk_f = [], []
+            for lo in range(0, n_reads, sub):
+                n = min(sub, n_reads - lo)
+                seg = d_bases[lo * L:(lo + n) * L]
+                pad = (-seg.numel()) % 16
+                codes = ((seg >> 1) & 3)
+                if pad:
+                    codes = torch.cat([codes, torch.zeros(pad, dtype=torch.uint8, device=dev)])
+                w = torch.empty(codes.numel() // 16, dtype=torch.int32, device=dev)
+                CH = 1 << 24
+                c16 = codes.view(-1, 16)
+                for a in range(0, c16.shape[0], CH):
+                    w[a:a + CH] = ((c16[a:a + CH].to(torch.int64) << shifts).sum(1) & 0xFFFFFFFF).to(torch.int32)
+                flag = (seg.view(n, L) == ord("N")).any(1)
+                fpad = (-n) % 32
+                if fpad:
+                    flag = torch.cat([flag, torch.zeros(fpad, dtype=torch.bool, device=dev)])
+                fw = ((flag.view(-1, 32).to(torch.int64) << torch.arange(32, device=dev, dtype=torch.int64)).sum(1)
+                      & 0xFFFFFFFF).to(torch.int32)
+                pk_w.append(w.cpu().pin_memory())
+                pk_f.append(fw.cpu().pin_memory())
+                del codes, c16, w, flag, fw
+            torch.cuda.synchronize()
+            pb = [(pk_w[i].data_ptr(), min(sub, n_reads - lo) * L, h_off.data_ptr(), h_bc.data_ptr() + 4 * lo,
+                   pk_f[i].data_ptr(), min(sub, n_reads - lo)) for i, lo in enumerate(range(0, n_reads, sub))]
+
+            def step_packed():
+                for b in pb:
+                    eng.submit_batch_packed_ptr(*b)
+                return eng.finish(nb, want_counts=(rank == 0))
+
+            for _ in range(2):
+                eng.reset_counts()
+                c_p = step_packed()
+            eng.reset_counts()
+            barrier()
+            t = time.perf_counter()
+            for _ in range(args.steps):
+                c_p = step_packed()
+            eng.sync()
+            dtp = max_over_ranks((time.perf_counter() - t) / args.steps)
+            barrier()
+            if rank == 0:
+                assert (c_p == counts).all(), "packed host-buffer path and device-resident path disagree"
+            h2d_p = sum(w.numel() * 4 for w in pk_w) + sum(f.numel() * 4 for f in pk_f) + sum(b[5] + 1 for b in pb) * 4 \
+                + n_reads * 4
+            e2e["packed"] = {"value": world * P / dtp, "unit": UNIT, "h2d_bytes_per_step": int(h2d_p),
+                             "d2h_bytes_per_step": int(nb * 8), "ms_per_step": dtp * 1e3,
+                             "path": "hast_submit_batch_packed: 2-bit words + containN bits as bin/classify's parser "
+                                     "emits them by default (packing happens while parsing, outside this region)"}
+            del pk_w, pk_f
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -68,6 +68,8 @@ SIGNATURES = {
     "hast_submit_batch": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32, C.POINTER(_u64)]),
     "hast_wait_copied": (_i32, [_vp, _u64]),
     "hast_submit_batch_device": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32]),
+    "hast_submit_batch_packed": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _u32, C.POINTER(_u64)]),
+    "hast_submit_batch_packed_device": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _u32]),
     "hast_sync": (_i32, [_vp]),
     "hast_finish": (_i32, [_vp, _vp, _u64]),
     "hast_stats_get": (_i32, [_vp, C.POINTER(Stats)]),
@@ -114,6 +116,27 @@ def _ptr(a: np.ndarray | None):
 def _arr(a, dtype) -> np.ndarray:
     a = np.ascontiguousarray(a, dtype=dtype)
     return a
+
+
+def pack_bases(bases: np.ndarray, read_off: np.ndarray):
+    """Host-side form of hast_submit_batch_packed: (uint32 words, 16 bases each, first base in the top
+    two bits; has_n bit mask, one bit per read).  numpy restatement of what the C++ parser emits."""
+    bases = np.ascontiguousarray(bases, np.uint8).reshape(-1)
+    n = bases.size
+    codes = ((bases >> 1) & 3).astype(np.uint32)
+    pad = (-n) % 16
+    if pad:
+        codes = np.concatenate([codes, np.zeros(pad, np.uint32)])
+    sh = (30 - 2 * np.arange(16, dtype=np.uint32)).astype(np.uint32)
+    words = (codes.reshape(-1, 16) << sh).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+    n_reads = read_off.size - 1
+    is_n = np.concatenate([[0], np.cumsum(bases == ord("N"), dtype=np.int64)])
+    off = read_off.astype(np.int64)
+    flag = (is_n[off[1:]] - is_n[off[:-1]]) > 0
+    bits = np.zeros(((n_reads + 31) // 32) * 32, np.uint8)
+    bits[:n_reads] = flag
+    has_n = np.packbits(bits.reshape(-1, 32)[:, ::-1], axis=1).view(">u4").astype(np.uint32).reshape(-1)
+    return np.ascontiguousarray(words), np.ascontiguousarray(has_n if has_n.size else np.zeros(1, np.uint32))
 
 
 class Engine:
@@ -214,6 +237,29 @@ class Engine:
         t = C.c_uint64()
         self._ck(self.lib.hast_submit_batch(self._ctx, bases_ptr, n_bases, off_ptr, bc_ptr, n_reads, C.byref(t)))
         return t.value
+
+    def submit_batch_packed(self, bases: np.ndarray, read_off: np.ndarray, barcode_id: np.ndarray) -> int:
+        """ASCII in, packed on the host here (pack_bases) and submitted through hast_submit_batch_packed."""
+        bases = _arr(bases, np.uint8).reshape(-1)
+        read_off = _arr(read_off, np.uint32)
+        barcode_id = _arr(barcode_id, np.uint32)
+        packed, has_n = pack_bases(bases, read_off)
+        t = C.c_uint64()
+        self._ck(self.lib.hast_submit_batch_packed(self._ctx, _ptr(packed), bases.size, _ptr(read_off),
+                                                   _ptr(barcode_id), _ptr(has_n), barcode_id.size, C.byref(t)))
+        self._ck(self.lib.hast_wait_copied(self._ctx, t.value))
+        return t.value
+
+    def submit_batch_packed_ptr(self, packed_ptr: int, n_bases: int, off_ptr: int, bc_ptr: int, hasn_ptr: int,
+                                n_reads: int) -> int:
+        t = C.c_uint64()
+        self._ck(self.lib.hast_submit_batch_packed(self._ctx, packed_ptr, n_bases, off_ptr, bc_ptr, hasn_ptr,
+                                                   n_reads, C.byref(t)))
+        return t.value
+
+    def submit_batch_packed_device(self, packed_ptr, n_bases, off_ptr, bc_ptr, hasn_ptr, n_reads):
+        self._ck(self.lib.hast_submit_batch_packed_device(self._ctx, packed_ptr, n_bases, off_ptr, bc_ptr,
+                                                          hasn_ptr, n_reads))
 
     def wait_copied(self, ticket: int):
         self._ck(self.lib.hast_wait_copied(self._ctx, ticket))

@@ -140,7 +140,9 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 // KT > 0: k is the compile-time constant KT (shift amounts fold into immediates); KT == 0: any k in 1..32.
-template <int KT, bool TMA>
+// PACKED: the batch arrives 2-bit packed from the host parser (a quarter of the PCIe bytes); phase (a)
+// is then a plain copy of words and containN comes from the per-read flag the parser set.
+template <int KT, bool TMA, bool PACKED = false>
 __global__ void __launch_bounds__(kTileThreads, 4)
 classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_barcodes,
                 DevStats* __restrict__ stats) {
@@ -236,7 +238,14 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
             // (a) pack: 16 ASCII bytes -> one 2-bit word; 'N' bytes flagged
             for (uint32_t seg = tid; seg < nseg + 4; seg += kTileThreads) {
                 uint32_t word = 0;
-                if (seg < nseg) {
+                if (PACKED) {
+                    if (seg < nseg) {
+                        const uint32_t gw = (lo >> 4) + seg;
+                        if ((uint64_t)gw * 16u < b.n_bases)
+                            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;"
+                                         : "=r"(word) : "l"(b.packed + gw), "l"(pol_first));
+                    }
+                } else if (seg < nseg) {
                     uint4 v;
                     if (TMA) {
                         v = *reinterpret_cast<const uint4*>(sm.raw + 16u * seg);
@@ -277,7 +286,9 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
             // (b) per read: containN (classify.cpp:182-185), positions that start no k-mer
             for (uint32_t r = ra + tid; r < rb; r += kTileThreads) {
                 const uint32_t s = s_off[r] - lo, e = s_off[r + 1] - lo, L = e - s;
-                if (any_bits(s_bad, s, e)) {               // classify.cpp:190-193: no votes at all
+                const bool has_n = PACKED ? ((b.has_n[(r0 + r) >> 5] >> ((r0 + r) & 31u)) & 1u) != 0u
+                                          : any_bits(s_bad, s, e);
+                if (has_n) {                               // classify.cpp:190-193: no votes at all
                     ++st_n;
                     set_bits(s_bad, s, e);
                 } else if (L < (uint32_t)k) {              // kmer.h:171 assert in the reference

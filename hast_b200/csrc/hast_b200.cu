@@ -30,6 +30,7 @@ struct Slot {
     uint8_t* d_bases = nullptr;  size_t cap_bases = 0;
     uint32_t* d_off = nullptr;   size_t cap_off = 0;
     uint32_t* d_bc = nullptr;    size_t cap_bc = 0;
+    uint32_t* d_hasn = nullptr;  size_t cap_hasn = 0;
     cudaEvent_t copied = nullptr, done = nullptr;
 };
 
@@ -163,12 +164,14 @@ int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv, uint64_t* d_kmers,
     const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->tile_blocks);
     if (mode == MODE_CLASSIFY && ctx->opt_kernel >= 1) {
         const uint32_t n_ftiles = (bv.n_reads + kFusedReadsPerTile - 1) / kFusedReadsPerTile;
-        const bool tma = ctx->opt_kernel == 2;
+        const bool tma = ctx->opt_kernel == 2 && !bv.packed;
         const int fgrid = (int)std::min<uint32_t>(n_ftiles, (uint32_t)(tma ? ctx->fused_blocks_tma : ctx->fused_blocks));
         const uint32_t nbc = (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull);
 #define HAST_LAUNCH_K(KT)                                                                                         \
     do {                                                                                                          \
-        if (tma) classify_kernel<KT, true><<<fgrid, kTileThreads, sizeof(FusedSmem<true>), ctx->cs>>>(            \
+        if (bv.packed) classify_kernel<KT, false, true><<<fgrid, kTileThreads, sizeof(FusedSmem<false>), ctx->cs>>>( \
+                ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                                   \
+        else if (tma) classify_kernel<KT, true><<<fgrid, kTileThreads, sizeof(FusedSmem<true>), ctx->cs>>>(       \
                 ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                                   \
         else classify_kernel<KT, false><<<fgrid, kTileThreads, sizeof(FusedSmem<false>), ctx->cs>>>(              \
                 ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                                   \
@@ -242,7 +245,9 @@ int hast_create(int device, hast_ctx** out) {
     CU_NEW(cudaFuncSetAttribute(classify_kernel<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                 (int)sizeof(FusedSmem<false>)));                                                   \
     CU_NEW(cudaFuncSetAttribute(classify_kernel<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                (int)sizeof(FusedSmem<true>)));
+                                (int)sizeof(FusedSmem<true>)));                                                    \
+    CU_NEW(cudaFuncSetAttribute(classify_kernel<KT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                (int)sizeof(FusedSmem<false>)));
     HAST_ATTR(0) HAST_ATTR(17) HAST_ATTR(21) HAST_ATTR(25) HAST_ATTR(31)
 #undef HAST_ATTR
     int per_sm_f = 0, per_sm_t = 0;
@@ -264,7 +269,7 @@ void hast_destroy(hast_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     for (auto& s : ctx->slot) {
-        cudaFree(s.d_bases); cudaFree(s.d_off); cudaFree(s.d_bc);
+        cudaFree(s.d_bases); cudaFree(s.d_off); cudaFree(s.d_bc); cudaFree(s.d_hasn);
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -554,7 +559,7 @@ int hast_submit_batch(hast_ctx* ctx, const uint8_t* bases, uint64_t n_bases, con
     CU(cudaMemcpyAsync(s.d_bc, barcode_id, (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->hs));
     CU(cudaEventRecord(s.copied, ctx->hs));
     CU(cudaStreamWaitEvent(ctx->cs, s.copied, 0));
-    BatchView bv{s.d_bases, s.d_off, s.d_bc, n_bases, n_reads};
+    BatchView bv{s.d_bases, s.d_off, s.d_bc, n_bases, n_reads, nullptr, nullptr};
     if ((rc = launch_tile(ctx, MODE_CLASSIFY, bv, nullptr, nullptr))) return rc;
     CU(cudaEventRecord(s.done, ctx->cs));
     ctx->st.h2d_bytes += n_bases + ((size_t)n_reads + 1) * 4 + (size_t)n_reads * 4;
@@ -580,7 +585,58 @@ int hast_submit_batch_device(hast_ctx* ctx, const uint8_t* d_bases, uint64_t n_b
     if (!n_reads) return HAST_OK;
     if ((uintptr_t)d_bases & 15) return fail(ctx, HAST_E_ARG, "d_bases must be 16-byte aligned");
     CU(cudaSetDevice(ctx->device));
-    BatchView bv{d_bases, d_read_off, d_barcode_id, n_bases, n_reads};
+    BatchView bv{d_bases, d_read_off, d_barcode_id, n_bases, n_reads, nullptr, nullptr};
+    if ((rc = launch_tile(ctx, MODE_CLASSIFY, bv, nullptr, nullptr))) return rc;
+    ctx->st.batches++;
+    ctx->st.reads += n_reads;
+    ctx->st.bases += n_bases;
+    return HAST_OK;
+}
+
+// ---- host-packed batches -----------------------------------------------------
+int hast_submit_batch_packed(hast_ctx* ctx, const uint32_t* packed, uint64_t n_bases, const uint32_t* read_off,
+                             const uint32_t* barcode_id, const uint32_t* has_n, uint32_t n_reads, uint64_t* ticket) {
+    int rc = batch_args_ok(ctx, packed, read_off, barcode_id, n_bases, n_reads);
+    if (rc) return rc;
+    if (n_reads && !has_n) return fail(ctx, HAST_E_ARG, "NULL batch array");
+    if (ctx->opt_kernel == 0) return fail(ctx, HAST_E_STATE, "packed batches need the pre-filtered kernel (option kernel >= 1)");
+    if (ticket) *ticket = ctx->seq;
+    if (!n_reads) return HAST_OK;
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[ctx->seq % kSlots];
+    CU(cudaEventSynchronize(s.done));
+    const size_t n_words = (size_t)((n_bases + 15) / 16), n_flag = ((size_t)n_reads + 31) / 32;
+    if ((rc = ensure(ctx, (void**)&s.d_bases, &s.cap_bases, n_words * 4 + 16))) return rc;
+    if ((rc = ensure(ctx, (void**)&s.d_off, &s.cap_off, ((size_t)n_reads + 1) * 4))) return rc;
+    if ((rc = ensure(ctx, (void**)&s.d_bc, &s.cap_bc, (size_t)n_reads * 4))) return rc;
+    if ((rc = ensure(ctx, (void**)&s.d_hasn, &s.cap_hasn, n_flag * 4))) return rc;
+    CU(cudaMemcpyAsync(s.d_bases, packed, n_words * 4, cudaMemcpyHostToDevice, ctx->hs));
+    CU(cudaMemcpyAsync(s.d_off, read_off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, ctx->hs));
+    CU(cudaMemcpyAsync(s.d_bc, barcode_id, (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->hs));
+    CU(cudaMemcpyAsync(s.d_hasn, has_n, n_flag * 4, cudaMemcpyHostToDevice, ctx->hs));
+    CU(cudaEventRecord(s.copied, ctx->hs));
+    CU(cudaStreamWaitEvent(ctx->cs, s.copied, 0));
+    BatchView bv{nullptr, s.d_off, s.d_bc, n_bases, n_reads, (const uint32_t*)s.d_bases, s.d_hasn};
+    if ((rc = launch_tile(ctx, MODE_CLASSIFY, bv, nullptr, nullptr))) return rc;
+    CU(cudaEventRecord(s.done, ctx->cs));
+    ctx->st.h2d_bytes += n_words * 4 + ((size_t)n_reads + 1) * 4 + (size_t)n_reads * 4 + n_flag * 4;
+    ctx->st.batches++;
+    ctx->st.reads += n_reads;
+    ctx->st.bases += n_bases;
+    ctx->seq++;
+    return HAST_OK;
+}
+
+int hast_submit_batch_packed_device(hast_ctx* ctx, const uint32_t* d_packed, uint64_t n_bases,
+                                    const uint32_t* d_read_off, const uint32_t* d_barcode_id,
+                                    const uint32_t* d_has_n, uint32_t n_reads) {
+    int rc = batch_args_ok(ctx, d_packed, d_read_off, d_barcode_id, n_bases, n_reads);
+    if (rc) return rc;
+    if (n_reads && !d_has_n) return fail(ctx, HAST_E_ARG, "NULL batch array");
+    if (ctx->opt_kernel == 0) return fail(ctx, HAST_E_STATE, "packed batches need the pre-filtered kernel (option kernel >= 1)");
+    if (!n_reads) return HAST_OK;
+    CU(cudaSetDevice(ctx->device));
+    BatchView bv{nullptr, d_read_off, d_barcode_id, n_bases, n_reads, d_packed, d_has_n};
     if ((rc = launch_tile(ctx, MODE_CLASSIFY, bv, nullptr, nullptr))) return rc;
     ctx->st.batches++;
     ctx->st.reads += n_reads;
@@ -719,7 +775,7 @@ int hast_extract_kmers_device(hast_ctx* ctx, const uint8_t* d_bases, uint64_t n_
     if ((uintptr_t)d_bases & 15) return fail(ctx, HAST_E_ARG, "d_bases must be 16-byte aligned");
     if (n_bases >= 0xFFFFFFF0ull) return fail(ctx, HAST_E_ARG, "batch larger than 4 GiB of bases");
     CU(cudaSetDevice(ctx->device));
-    BatchView bv{d_bases, d_read_off, nullptr, n_bases, n_reads};
+    BatchView bv{d_bases, d_read_off, nullptr, n_bases, n_reads, nullptr, nullptr};
     return launch_tile(ctx, MODE_EXTRACT, bv, d_kmers_out, d_has_n_out);
 }
 

@@ -33,11 +33,15 @@ struct DevStats {
 };
 
 struct BatchView {
-    const uint8_t* bases;         // 16-byte aligned
-    const uint32_t* read_off;     // n_reads + 1
+    const uint8_t* bases;         // 16-byte aligned ASCII, or null when `packed` is used
+    const uint32_t* read_off;     // n_reads + 1 (byte offsets == base offsets)
     const uint32_t* barcode_id;   // n_reads (may be null for MODE_EXTRACT)
     uint64_t n_bases;
     uint32_t n_reads;
+    // host-packed form (hast_submit_batch_packed): the same base stream, 16 bases per word,
+    // first base in the top two bits, reads back to back; bit i of has_n = read i contains 'N'
+    const uint32_t* packed;
+    const uint32_t* has_n;
 };
 
 constexpr int kTileThreads = 256;

@@ -65,6 +65,7 @@ int parse_options(int argc, char** argv, Options& opt) {
     static const char optstring[] = "p:m:l:r:t:w:u:f:q:h";
     if (const char* e = getenv("HAST_GPUS")) opt.gpus = atoi(e);
     if (const char* e = getenv("HAST_STATS_JSON")) opt.stats_json = e;
+    if (const char* e = getenv("HAST_PACKED")) opt.packed_h2d = atoi(e) != 0;
     if (const char* e = getenv("HAST_BLOCK_MB")) opt.batch_bytes = (size_t)atol(e) << 20;
     optind = 1;
     for (;;) {

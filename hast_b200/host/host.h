@@ -29,6 +29,7 @@ struct Options {
     bool split_barcodes = false;           // also write the three *.unique.barcodes lists (script :156-162)
     bool partition_reads = false;          // also partition every input FASTQ (script :176-185); implies split
     std::string outdir;                    // where those files go ("" = cwd, like the script)
+    bool packed_h2d = true;                // parser packs to 2 bits before the copy (env HAST_PACKED=0: ASCII)
     size_t batch_bytes = 8u << 20;         // raw FASTQ text per parse block
 };
 // returns 0 to run, otherwise the process exit code (255 after printing usage)
@@ -80,6 +81,10 @@ struct Batch {
     uint32_t n_reads = 0;
     uint32_t max_barcode = 0;
     std::string error;
+    // packed mode (hast_submit_batch_packed): the parser emits 2-bit words + a containN bit per
+    // read instead of the ASCII bases -- a quarter of the pinned-memory and PCIe traffic
+    uint32_t* packed = nullptr;   size_t cap_words = 0;
+    uint32_t* has_n = nullptr;    // (cap_reads + 31) / 32 words
 };
 
 // classify.cpp:112-119
@@ -97,6 +102,9 @@ inline void parse_name(const char* head, size_t len, size_t& start, size_t& blen
 // Parse one block into a batch.  Returns false on a framing error that the
 // reference would have died on (message in batch.error).
 bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out);
+// Append `n` ASCII bases to a 2-bit MSB-first stream (kmer.h:11 code, kmer.h:156-160 order).
+// `acc`/`nbits` carry the partially filled word between calls; returns true if an 'N' was seen.
+bool pack_append(const char* seq, size_t n, uint32_t* words, size_t& n_words, uint64_t& acc, unsigned& nbits);
 
 // ---- haplotype call + table output (classify.cpp:66-102) ----------------------
 int get_hap(const std::string& barcode, int c0, int c1, uint64_t n0, uint64_t n1, double w0, double w1);

@@ -205,21 +205,29 @@ int run_classify(const Options& opt, RunStats& st) {
     for (auto& b : batch_pool) {
         b.cap_bases = block_bytes + 4096;
         b.cap_reads = block_bytes / 24 + 16;
-        void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+        void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
+        const bool packed = opt.packed_h2d && !parse_only;
+        b.cap_words = b.cap_bases / 16 + 2;
         if (parse_only) {
             p0 = malloc(b.cap_bases); p1 = malloc((b.cap_reads + 1) * 4); p2 = malloc(b.cap_reads * 4);
-        } else if (hast_host_alloc(&p0, b.cap_bases) || hast_host_alloc(&p1, (b.cap_reads + 1) * 4) ||
-                   hast_host_alloc(&p2, b.cap_reads * 4)) {
+        } else if (hast_host_alloc(&p0, packed ? b.cap_words * 4 : b.cap_bases) ||
+                   hast_host_alloc(&p1, (b.cap_reads + 1) * 4) || hast_host_alloc(&p2, b.cap_reads * 4) ||
+                   (packed && hast_host_alloc(&p3, (b.cap_reads / 32 + 2) * 4))) {
             alloc_ok = false;
             break;
         }
-        b.bases = (uint8_t*)p0; b.read_off = (uint32_t*)p1; b.barcode_id = (uint32_t*)p2;
+        if (packed) { b.packed = (uint32_t*)p0; b.has_n = (uint32_t*)p3; }
+        else b.bases = (uint8_t*)p0;
+        b.read_off = (uint32_t*)p1; b.barcode_id = (uint32_t*)p2;
         q_batch_free.push(&b);
     }
     auto free_batches = [&] {
         for (auto& b : batch_pool) {
             if (parse_only) { free(b.bases); free(b.read_off); free(b.barcode_id); }
-            else { hast_host_free(b.bases); hast_host_free(b.read_off); hast_host_free(b.barcode_id); }
+            else {
+                hast_host_free(b.bases); hast_host_free(b.packed); hast_host_free(b.has_n);
+                hast_host_free(b.read_off); hast_host_free(b.barcode_id);
+            }
         }
     };
     if (!alloc_ok) {
@@ -313,7 +321,10 @@ int run_classify(const Options& opt, RunStats& st) {
                     if (hast_reserve_barcodes(c, reserved) != HAST_OK) { sh.fail(hast_last_error(c)); abort_all(); break; }
                 }
                 uint64_t ticket = 0;
-                if (hast_submit_batch(c, b->bases, b->n_bases, b->read_off, b->barcode_id, b->n_reads, &ticket) != HAST_OK) {
+                const int src = b->packed
+                    ? hast_submit_batch_packed(c, b->packed, b->n_bases, b->read_off, b->barcode_id, b->has_n, b->n_reads, &ticket)
+                    : hast_submit_batch(c, b->bases, b->n_bases, b->read_off, b->barcode_id, b->n_reads, &ticket);
+                if (src != HAST_OK) {
                     sh.fail(hast_last_error(c)); abort_all(); break;
                 }
                 n_reads += b->n_reads;

@@ -134,6 +134,20 @@ int hast_wait_copied(hast_ctx *ctx, uint64_t ticket);
 int hast_submit_batch_device(hast_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases,
                              const uint32_t *d_read_off, const uint32_t *d_barcode_id,
                              uint32_t n_reads);
+/* The same batch as the host parser can hand it over when it packs while it
+ * parses: `packed` holds the concatenated reads at 2 bits per base with the
+ * reference's code (c & 6) >> 1 (kmer.h:11), 16 bases per 32-bit word, first
+ * base in the two most significant bits (kmer.h:156-160), reads back to back
+ * (no per-read alignment), the last word zero-padded; read_off[] counts BASES;
+ * bit (i & 31) of has_n[i >> 5] is set iff read i contains the byte 'N'
+ * (containN, classify.cpp:182-185) -- such a read casts no votes.  A quarter of
+ * the host-to-device bytes of hast_submit_batch; results are identical.       */
+int hast_submit_batch_packed(hast_ctx *ctx, const uint32_t *packed, uint64_t n_bases,
+                             const uint32_t *read_off, const uint32_t *barcode_id,
+                             const uint32_t *has_n, uint32_t n_reads, uint64_t *ticket);
+int hast_submit_batch_packed_device(hast_ctx *ctx, const uint32_t *d_packed, uint64_t n_bases,
+                                    const uint32_t *d_read_off, const uint32_t *d_barcode_id,
+                                    const uint32_t *d_has_n, uint32_t n_reads);
 int hast_sync(hast_ctx *ctx);
 
 /* ---- finish: collect the per-barcode counts ---------------------------- */

@@ -26,11 +26,14 @@ def run_cli(args, cwd=None, env=None):
     return subprocess.run([str(CLASSIFY)] + [str(a) for a in args], cwd=cwd, capture_output=True, env=e)
 
 
+@pytest.mark.parametrize("packed", ["1", "0"], ids=["packed_h2d", "ascii_h2d"])
 @pytest.mark.parametrize("name", CLASSIFY_CASES)
-def test_cli_matches_golden(name):
+def test_cli_matches_golden(name, packed):
+    """packed_h2d: the parser packs to 2 bits and submits through hast_submit_batch_packed (default);
+    ascii_h2d: the ASCII bases travel and the GPU packs them (HAST_PACKED=0)."""
     d = GOLDEN / name
     args = json.loads((d / "cmd.txt").read_text())
-    r = run_cli(args, cwd=d)
+    r = run_cli(args, cwd=d, env={"HAST_PACKED": packed})
     assert r.returncode == 0, r.stderr[-600:].decode(errors="replace")
     assert r.stdout == (d / "expected.tsv").read_bytes()
     if name == "adv_k21":                      # log lines users look for (classify.cpp:45,321)

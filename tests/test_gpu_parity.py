@@ -117,6 +117,34 @@ def test_fused_parity(engine, k):
     assert (got3 == want).all()
 
 
+@pytest.mark.parametrize("k", [5, 17, 21, 32])
+def test_packed_batches_equal_ascii_batches(engine, k, request):
+    """hast_submit_batch_packed (2-bit words + containN bits made on the host) == hast_submit_batch."""
+    from hast_b200.capi import HastError, E_STATE
+    case = cases.adversarial_case(k, 2500, seed=400 + k)
+    build_table(engine, case)
+    o, _ = build_oracle(case)
+    bases, off = cases.flatten(case["reads"])
+    nb = len(case["bc_names"])
+    want, lookups = o.classify_batch(bases, off, case["bc_ids"], nb)
+    engine.reset_counts()
+    engine.reserve_barcodes(nb)
+    n = len(case["reads"])
+    if "direct" in request.node.name and "prefilter" not in request.node.name:
+        with pytest.raises(HastError) as e:            # the direct-probe kernel has no packed form
+            engine.submit_batch_packed(bases, off.astype(np.uint32), case["bc_ids"])
+        assert e.value.code == E_STATE
+        return
+    cuts = [0, 1, 777, n]                              # ragged batches: packed streams restart per batch
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        engine.submit_batch_packed(bases[off[a]:off[b]], (off[a:b + 1] - off[a]).astype(np.uint32), case["bc_ids"][a:b])
+    got = engine.finish(nb)
+    st = engine.stats()
+    assert (got == want).all() and want.sum() > 0
+    assert st["lookups"] == lookups
+    assert st["reads_with_n"] == sum(b"N" in r for r in case["reads"])
+
+
 def test_fused_empty_and_minimal(engine):
     case = cases.adversarial_case(21, 50, seed=9)
     build_table(engine, case)
