@@ -30,14 +30,19 @@ $(TOOLS): hast_b200/tools/fastq_fmt.c
 	@mkdir -p hast_b200/lib
 	$(CC) -O2 -std=c11 -fPIC -shared $< -lz -o $@
 
-host: bin/classify bin/mergeResult bin/quartering_fastq
+host: bin/classify bin/mergeResult bin/quartering_fastq bin/classify_seq
 HOST_SRCS := $(wildcard $(HOST)/*.cpp)
 HOST_HDRS := $(wildcard $(HOST)/*.h)
-MAINS := $(HOST)/merge_result_main.cpp $(HOST)/quartering_main.cpp $(HOST)/classify_main.cpp
+MAINS := $(HOST)/merge_result_main.cpp $(HOST)/quartering_main.cpp $(HOST)/classify_main.cpp $(HOST)/classify_seq_main.cpp
 bin/classify: $(filter-out $(MAINS),$(HOST_SRCS)) $(HOST)/classify_main.cpp $(HOST_HDRS) $(LIB) include/hast_b200.h
 	@mkdir -p bin
 	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(filter-out $(MAINS),$(HOST_SRCS)) $(HOST)/classify_main.cpp \
 	    -Lhast_b200/lib -lhast_b200 -lz -Wl,-rpath,'$$ORIGIN/../hast_b200/lib' -o $@
+# stage 03's per-sequence classifier on the same engine
+bin/classify_seq: $(HOST)/classify_seq_main.cpp $(LIB) include/hast_b200.h
+	@mkdir -p bin
+	$(CXX) -O2 -g -std=c++17 -Wall -Iinclude $(HOST)/classify_seq_main.cpp -Lhast_b200/lib -lhast_b200 -lz \
+	    -Wl,-rpath,'$$ORIGIN/../hast_b200/lib' -o $@
 # the read partitioner alone needs no GPU and no CUDA library
 bin/quartering_fastq: $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/fastq_source.cpp $(HOST_HDRS)
 	@mkdir -p bin

@@ -142,7 +142,12 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 // KT > 0: k is the compile-time constant KT (shift amounts fold into immediates); KT == 0: any k in 1..32.
 // PACKED: the batch arrives 2-bit packed from the host parser (a quarter of the PCIe bytes); phase (a)
 // is then a plain copy of words and containN comes from the per-read flag the parser set.
-template <int KT, bool TMA, bool PACKED = false>
+// SEQ: the per-sequence classifier of stage 03 (03.mkoutput_by_fabulous2.0/src_main/classify.cpp:203-218).
+// That program matches k-mer STRINGS, so a window votes only if all its bytes are upper-case A/C/G/T
+// (the lists are jellyfish dumps: upper-case ACGT); a window over anything else ('N', lower case, '\r')
+// simply does not match -- it does not silence the rest of the sequence -- and a sequence shorter than
+// k is not an error.  "Reads" are chunks of a sequence, "barcodes" are sequence ids.
+template <int KT, bool TMA, bool PACKED = false, bool SEQ = false>
 __global__ void __launch_bounds__(kTileThreads, 4)
 classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_barcodes,
                 DevStats* __restrict__ stats) {
@@ -261,7 +266,11 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                         }
                     }
                     word = pack16(v);
-                    if (any_N4(v.x) | any_N4(v.y) | any_N4(v.z) | any_N4(v.w)) {
+                    if (SEQ) {
+                        const uint32_t m16 = not_acgt4(v.x) | (not_acgt4(v.y) << 4) | (not_acgt4(v.z) << 8) |
+                                             (not_acgt4(v.w) << 12);
+                        if (m16) atomicOr(&s_bad[seg >> 1], m16 << ((seg & 1u) * 16u));
+                    } else if (any_N4(v.x) | any_N4(v.y) | any_N4(v.z) | any_N4(v.w)) {
                         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
                         uint32_t m16 = 0;
                         for (uint32_t j = 0; j < 16; ++j)
@@ -283,12 +292,33 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                 continue;
             }
 
+            if (SEQ) {
+                // a byte that is not ACGT spoils the k windows that contain it: smear every flag over
+                // the k-1 positions before it.  Read boundaries need no care, the last k-1 positions
+                // of a read start no k-mer anyway.
+                uint32_t smeared[(FusedSmem<TMA>::kWords / 2 + 2 + kTileThreads - 1) / kTileThreads];
+                const uint32_t nbw = (nseg >> 1) + 1;
+                int it = 0;
+                for (uint32_t w = tid; w < nbw; w += kTileThreads, ++it) {
+                    const uint64_t pair = (uint64_t)s_bad[w] | ((uint64_t)s_bad[w + 1] << 32);
+                    uint64_t d = pair;
+                    for (int j = 1; j < k; ++j) d |= pair >> j;
+                    smeared[it] = (uint32_t)d;
+                }
+                __syncthreads();
+                it = 0;
+                for (uint32_t w = tid; w < nbw; w += kTileThreads, ++it) s_bad[w] = smeared[it];
+                __syncthreads();
+            }
             // (b) per read: containN (classify.cpp:182-185), positions that start no k-mer
             for (uint32_t r = ra + tid; r < rb; r += kTileThreads) {
                 const uint32_t s = s_off[r] - lo, e = s_off[r + 1] - lo, L = e - s;
-                const bool has_n = PACKED ? ((b.has_n[(r0 + r) >> 5] >> ((r0 + r) & 31u)) & 1u) != 0u
+                const bool has_n = SEQ ? false
+                                 : PACKED ? ((b.has_n[(r0 + r) >> 5] >> ((r0 + r) & 31u)) & 1u) != 0u
                                           : any_bits(s_bad, s, e);
-                if (has_n) {                               // classify.cpp:190-193: no votes at all
+                if (SEQ && L < (uint32_t)k) {              // stage 03: the loop over windows is simply empty
+                    set_bits(s_bad, s, e);
+                } else if (has_n) {                        // classify.cpp:190-193: no votes at all
                     ++st_n;
                     set_bits(s_bad, s, e);
                 } else if (L < (uint32_t)k) {              // kmer.h:171 assert in the reference

@@ -111,6 +111,7 @@ struct hast_ctx {
     uint64_t filt_words = 0;
     // options (hast_set_option)
     int64_t opt_kernel = 1;               // 1 = classify_kernel (pre-filter), 2 = same with TMA-staged reads, 0 = tile_kernel<MODE_CLASSIFY>
+    int64_t opt_seq_mode = 0;             // 1 = stage-03 window rule (classify_kernel<.., SEQ>)
     int64_t opt_filter_bits_per_key = 16;
     int64_t opt_filter_max_bytes = (int64_t)64 << 20;
     std::string err;
@@ -176,6 +177,11 @@ int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv, uint64_t* d_kmers,
         else classify_kernel<KT, false><<<fgrid, kTileThreads, sizeof(FusedSmem<false>), ctx->cs>>>(              \
                 ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                                   \
     } while (0)
+        if (ctx->opt_seq_mode) {
+            if (bv.packed) return fail(ctx, HAST_E_STATE, "seq_mode takes ASCII batches");
+            classify_kernel<0, false, false, true><<<fgrid, kTileThreads, sizeof(FusedSmem<false>), ctx->cs>>>(
+                ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);
+        } else
         switch (ctx->tv.k) {                      // specialised for HAST's default k and the benchmarked sweep
             case 17: HAST_LAUNCH_K(17); break;
             case 21: HAST_LAUNCH_K(21); break;
@@ -250,6 +256,8 @@ int hast_create(int device, hast_ctx** out) {
                                 (int)sizeof(FusedSmem<false>)));
     HAST_ATTR(0) HAST_ATTR(17) HAST_ATTR(21) HAST_ATTR(25) HAST_ATTR(31)
 #undef HAST_ATTR
+    CU_NEW(cudaFuncSetAttribute(classify_kernel<0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(FusedSmem<false>)));
     int per_sm_f = 0, per_sm_t = 0;
     CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, classify_kernel<0, false>, kTileThreads,
                                                          sizeof(FusedSmem<false>)));
@@ -292,7 +300,12 @@ int hast_set_option(hast_ctx* ctx, const char* name, int64_t value) {
     if (n == "kernel") {
         if (value < 0 || value > 2)
             return fail(ctx, HAST_E_ARG, "kernel: 0 (direct probe), 1 (pre-filter), 2 (pre-filter, TMA-staged reads)");
+        if (value == 0 && ctx->opt_seq_mode) return fail(ctx, HAST_E_STATE, "seq_mode needs the pre-filtered kernel");
         ctx->opt_kernel = value;
+    } else if (n == "seq_mode") {
+        if (value != 0 && value != 1) return fail(ctx, HAST_E_ARG, "seq_mode: 0 or 1");
+        if (value && ctx->opt_kernel == 0) return fail(ctx, HAST_E_STATE, "seq_mode needs the pre-filtered kernel");
+        ctx->opt_seq_mode = value;
     } else if (n == "filter_bits_per_key") {
         if (value < 1 || value > 64) return fail(ctx, HAST_E_ARG, "filter_bits_per_key: 1..64");
         ctx->opt_filter_bits_per_key = value;

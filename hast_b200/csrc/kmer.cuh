@@ -53,6 +53,17 @@ __device__ __forceinline__ bool any_N4(uint32_t w) {
     return ((x - 0x01010101u) & ~x & 0x80808080u) != 0u;
 }
 
+// 4-bit mask of the bytes of w that are NOT one of 'A' 'C' 'G' 'T' (upper case), exact per byte
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {       // 0x80 in every byte of x that is 0
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+__device__ __forceinline__ uint32_t not_acgt4(uint32_t w) {
+    const uint32_t good = zero_bytes(w ^ 0x41414141u) | zero_bytes(w ^ 0x43434343u) |
+                          zero_bytes(w ^ 0x47474747u) | zero_bytes(w ^ 0x54545454u);
+    const uint32_t bad = ~good & 0x80808080u;
+    return ((bad >> 7) * 0x00204081u >> 21) & 0xFu;                // bits 0,8,16,24 -> bits 0..3
+}
+
 // The 64 stream bits that start at base position p (p counted from the first
 // base of the packed tile): words are 16 bases each, MSB-first.
 __device__ __forceinline__ uint64_t window64(const uint32_t* __restrict__ s_packed, uint32_t p) {

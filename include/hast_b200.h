@@ -77,7 +77,11 @@ int          hast_device(const hast_ctx *ctx);
 /* Tuning knobs, set before hast_table_begin: "kernel" (1 = pre-filtered fused
  * kernel, default; 0 = direct table probe per position), "filter_bits_per_key"
  * (default 16), "filter_max_bytes" (default 64 MiB: the filter is meant to stay
- * L2-resident).  None of them changes any result.                              */
+ * L2-resident).  None of them changes any result.  "seq_mode" = 1 switches the
+ * fused kernel to the window rule of HAST stage 03 (03.mkoutput_by_fabulous2.0/
+ * src_main/classify.cpp:203-218, string k-mers): a k-mer position votes iff all
+ * its k bytes are upper-case A/C/G/T, other bytes do not silence the rest of the
+ * sequence, and sequences shorter than k are not an error.                     */
 int          hast_set_option(hast_ctx *ctx, const char *name, int64_t value);
 /* pinned host memory for batch buffers */
 int          hast_host_alloc(void **ptr, size_t bytes);
