@@ -78,15 +78,53 @@ WORKLOAD_TEXT = {
 # clocks during the timed region (B200_PROFILING.md)
 # ----------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML in-process every 2 ms
+    (the timed region is only tens of milliseconds), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.source = "nvidia-smi"
         self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+        self._t = threading.Thread(target=self._run_nvml if self._nvml else self._run_smi, daemon=True)
 
-    def _run(self):
+    def _run_nvml(self):
+        nv = self._nvml
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for n, b in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    def _run_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
@@ -112,7 +150,8 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "source": self.source}
 
 
 # ----------------------------------------------------------------------------
