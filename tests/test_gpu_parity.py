@@ -324,3 +324,29 @@ def test_permutation_invariance_cfg1_scale(engine):
     engine.reserve_barcodes(t.n_barcodes)
     engine.submit_batch(bases.reshape(-1, L)[perm], off, bc[perm])
     assert (engine.finish(t.n_barcodes) == want).all()
+
+
+def test_skewed_barcodes_parity(engine):
+    """configs[4] shape at a size the oracle finishes in seconds: heavy-tailed (Zipf 1.2) reads per barcode,
+    so a few barcodes take most of the per-barcode atomics while most barcodes see one or two reads."""
+    spec = synth.TrioSpec(genome_len=400_000, het=0.002, n_pairs=60_000, n_barcodes=40_000, zipf_alpha=1.2)
+    t = synth.make_trio(spec)
+    k = spec.k
+    top = np.bincount(t.pair_bc, minlength=t.n_barcodes).max()
+    assert top > 0.02 * spec.n_pairs                   # the tail really is heavy
+    engine.table_begin(k, t.pat.size + t.mat.size)
+    engine.table_add_packed(t.pat, 0)
+    engine.table_add_packed(t.mat, 1)
+    o = orc.Oracle()
+    o.load_kmers(t.kmer_text(0), 0)
+    o.load_kmers(t.kmer_text(1), 1)
+    bases, off, bc = t.batch()
+    want, lookups = o.classify_batch(bases, off.astype(np.uint64), bc, t.n_barcodes, nthreads=8)
+    engine.reset_counts()
+    engine.reserve_barcodes(t.n_barcodes)
+    # reads grouped by barcode: the worst case for atomic contention on the hot barcodes
+    order = np.argsort(bc, kind="stable")
+    L = spec.read_len
+    engine.submit_batch(bases.reshape(-1, L)[order], off, bc[order])
+    got = engine.finish(t.n_barcodes)
+    assert (got == want).all() and engine.stats()["lookups"] == lookups
