@@ -205,14 +205,11 @@ def _unique_sets(p_list, m_list, device):
     return pat, mat
 
 
-def make_trio(spec: TrioSpec, device: str = "cpu", keep_reads_on_device: bool = False) -> Trio:
-    if spec.k > 31 and device != "cpu":
-        raise ValueError("torch path supports k <= 31")
-    G, k, L = spec.genome_len, spec.k, spec.read_len
-    base_seed = spec.seed
-    rng = lambda s: np.random.Generator(np.random.PCG64(base_seed * 1000 + s))
-
-    # 1. ancestor and the four parental haplotypes
+def _haplotypes(spec: TrioSpec) -> dict:
+    """Ancestor genome (i.i.d. uniform) and the four parental haplotypes P1 P2 M1 M2, each the ancestor
+    with independent SNPs at rate spec.het.  Codes A0 C1 T2 G3."""
+    G = spec.genome_len
+    rng = lambda s: np.random.Generator(np.random.PCG64(spec.seed * 1000 + s))
     anc = rng(1).integers(0, 4, G, dtype=np.uint8)
     haps = {}
     for name, s in (("P1", 11), ("P2", 12), ("M1", 21), ("M2", 22)):
@@ -222,6 +219,66 @@ def make_trio(spec: TrioSpec, device: str = "cpu", keep_reads_on_device: bool = 
         h = anc.copy()
         h[pos] = (h[pos] + g.integers(1, 4, n_snp, dtype=np.uint8)) & 3
         haps[name] = h
+    return haps
+
+
+def parent_reads(spec: TrioSpec, coverage: float, read_len: int = 100, err: float = 0.003, n_frac: float = 0.01,
+                 lowercase_frac: float = 0.01, seed: int = 61) -> dict:
+    """Whole-genome shotgun reads of the two parents, the input of HAST stage 00
+    (00.build_unshare_kmers_by_jellyfish/build_unshared_kmers.sh --paternal / --maternal): each parent is
+    sequenced to `coverage` x in total, half from each of its haplotypes, either strand, substitution errors at
+    rate `err`, a fraction of reads with one 'N', a fraction in lower case.
+    -> {"paternal": uint8 [n, L] ASCII, "maternal": ...}"""
+    haps = _haplotypes(spec)
+    G, L = spec.genome_len, read_len
+    out = {}
+    for pi, (parent, names) in enumerate((("paternal", ("P1", "P2")), ("maternal", ("M1", "M2")))):
+        g = np.random.Generator(np.random.PCG64(spec.seed * 1000 + seed + pi))
+        n = int(coverage * G / L)
+        which = g.integers(0, 2, n)
+        start = g.integers(0, G - L + 1, n)
+        codes = np.empty((n, L), np.uint8)
+        for h in (0, 1):
+            sel = np.nonzero(which == h)[0]
+            codes[sel] = np.lib.stride_tricks.sliding_window_view(haps[names[h]], L)[start[sel]]
+        rev = g.random(n) < 0.5
+        codes[rev] = (codes[rev] ^ 2)[:, ::-1]
+        n_err = int(g.binomial(n * L, err))
+        flat = codes.reshape(-1)
+        ep = g.integers(0, n * L, n_err)
+        flat[ep] = (flat[ep] + g.integers(1, 4, n_err, dtype=np.uint8)) & 3
+        reads = LETTERS[codes]
+        with_n = np.nonzero(g.random(n) < n_frac)[0]
+        reads[with_n, g.integers(0, L, with_n.size)] = ord("N")
+        low = g.random(n) < lowercase_frac
+        reads[low] |= 0x20
+        out[parent] = reads
+    return out
+
+
+def write_reads_fastq(path, reads: np.ndarray, gz: bool = False, prefix: str = "r") -> str:
+    """Plain 4-line FASTQ of an [n, L] ASCII array (parental WGS reads carry no barcode)."""
+    import gzip
+    n, L = reads.shape
+    qual = b"F" * L
+    chunks = []
+    for i in range(n):
+        chunks.append(b"@%s%d\n%s\n+\n%s\n" % (prefix.encode(), i, reads[i].tobytes(), qual))
+    data = b"".join(chunks)
+    with (gzip.open(path, "wb", compresslevel=1) if gz else open(path, "wb")) as f:
+        f.write(data)
+    return str(path)
+
+
+def make_trio(spec: TrioSpec, device: str = "cpu", keep_reads_on_device: bool = False) -> Trio:
+    if spec.k > 31 and device != "cpu":
+        raise ValueError("torch path supports k <= 31")
+    G, k, L = spec.genome_len, spec.k, spec.read_len
+    base_seed = spec.seed
+    rng = lambda s: np.random.Generator(np.random.PCG64(base_seed * 1000 + s))
+
+    # 1. ancestor and the four parental haplotypes
+    haps = _haplotypes(spec)
 
     # 2. parent-unique canonical k-mers (exact set difference)
     if device == "cpu":
