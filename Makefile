@@ -20,7 +20,7 @@ HOST := hast_b200/host
 all: lib tools host oracle
 
 lib: $(LIB)
-$(LIB): $(CSRC)/hast_b200.cu $(CSRC)/kernels.cuh $(CSRC)/fused.cuh $(CSRC)/table.cuh $(CSRC)/kmer.cuh include/hast_b200.h
+$(LIB): $(CSRC)/hast_b200.cu $(CSRC)/kcount.cuh $(CSRC)/kernels.cuh $(CSRC)/fused.cuh $(CSRC)/table.cuh $(CSRC)/kmer.cuh include/hast_b200.h
 	@mkdir -p hast_b200/lib
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared $< -o $@ -ldl 2> hast_b200/lib/ptxas.log || (cat hast_b200/lib/ptxas.log; exit 1)
 	@grep -E "registers|spill" hast_b200/lib/ptxas.log | sort | uniq -c | sort -rn | head -20 || true
@@ -30,10 +30,10 @@ $(TOOLS): hast_b200/tools/fastq_fmt.c
 	@mkdir -p hast_b200/lib
 	$(CC) -O2 -std=c11 -fPIC -shared $< -lz -o $@
 
-host: bin/classify bin/mergeResult bin/quartering_fastq bin/classify_seq
+host: bin/classify bin/mergeResult bin/quartering_fastq bin/classify_seq bin/build_unshared_kmers
 HOST_SRCS := $(wildcard $(HOST)/*.cpp)
 HOST_HDRS := $(wildcard $(HOST)/*.h)
-MAINS := $(HOST)/merge_result_main.cpp $(HOST)/quartering_main.cpp $(HOST)/classify_main.cpp $(HOST)/classify_seq_main.cpp
+MAINS := $(HOST)/merge_result_main.cpp $(HOST)/quartering_main.cpp $(HOST)/classify_main.cpp $(HOST)/classify_seq_main.cpp $(HOST)/build_unshared_main.cpp
 bin/classify: $(filter-out $(MAINS),$(HOST_SRCS)) $(HOST)/classify_main.cpp $(HOST_HDRS) $(LIB) include/hast_b200.h
 	@mkdir -p bin
 	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(filter-out $(MAINS),$(HOST_SRCS)) $(HOST)/classify_main.cpp \
@@ -42,6 +42,11 @@ bin/classify: $(filter-out $(MAINS),$(HOST_SRCS)) $(HOST)/classify_main.cpp $(HO
 bin/classify_seq: $(HOST)/classify_seq_main.cpp $(LIB) include/hast_b200.h
 	@mkdir -p bin
 	$(CXX) -O2 -g -std=c++17 -Wall -Iinclude $(HOST)/classify_seq_main.cpp -Lhast_b200/lib -lhast_b200 -lz \
+	    -Wl,-rpath,'$$ORIGIN/../hast_b200/lib' -o $@
+# stage 00's parent-unique k-mer lists from parental reads (count table on the GPU)
+bin/build_unshared_kmers: $(HOST)/build_unshared_main.cpp $(LIB) include/hast_b200.h
+	@mkdir -p bin
+	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(HOST)/build_unshared_main.cpp -Lhast_b200/lib -lhast_b200 -lz \
 	    -Wl,-rpath,'$$ORIGIN/../hast_b200/lib' -o $@
 # the read partitioner alone needs no GPU and no CUDA library
 bin/quartering_fastq: $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/fastq_source.cpp $(HOST_HDRS)

@@ -44,6 +44,12 @@ class Stats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class KcInfo(C.Structure):
+    _fields_ = [("k", C.c_int32), ("part", C.c_uint32), ("n_parts", C.c_uint32), ("n_slots", C.c_uint64),
+                ("bytes", C.c_uint64), ("occupied", C.c_uint64), ("distinct", C.c_uint64 * 2), ("both", C.c_uint64),
+                ("occurrences", C.c_uint64 * 2), ("windows", C.c_uint64), ("table_full", C.c_uint64)]
+
+
 _vp, _u64, _u32, _i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
 
 # name -> (restype, argtypes): every symbol include/hast_b200.h declares
@@ -84,6 +90,14 @@ SIGNATURES = {
     "hast_extract_kmers_device": (_i32, [_vp, _vp, _u64, _vp, _u32, _vp, _vp]),
     "hast_lookup_device": (_i32, [_vp, _vp, _u64, _vp]),
     "hast_gather_roofline": (_i32, [_vp, _u64, _u64, C.POINTER(C.c_float)]),
+    "hast_kc_begin": (_i32, [_vp, _i32, _u64, _u32, _u32]),
+    "hast_kc_add": (_i32, [_vp, _vp, _u64, _vp, _u32, _i32, C.POINTER(_u64)]),
+    "hast_kc_add_device": (_i32, [_vp, _vp, _u64, _vp, _u32, _i32]),
+    "hast_kc_info_get": (_i32, [_vp, C.POINTER(KcInfo)]),
+    "hast_kc_histo": (_i32, [_vp, _i32, _u32, _vp]),
+    "hast_kc_select": (_i32, [_vp, _i32, _u32, _u32, _i32, _vp, _u64, C.POINTER(_u64)]),
+    "hast_kc_to_table": (_i32, [_vp, _vp, _u32, _u32, _u32, _u32]),
+    "hast_kc_end": (_i32, [_vp]),
 }
 
 _lib = None
@@ -333,3 +347,55 @@ class Engine:
         g = C.c_float()
         self._ck(self.lib.hast_gather_roofline(self._ctx, int(n_probes), int(span_bytes), C.byref(g)))
         return g.value
+
+    # -- stage 00: k-mer counting -----------------------------------------------
+    def kc_begin(self, k: int, expected_distinct: int, part: int = 0, n_parts: int = 1):
+        self._ck(self.lib.hast_kc_begin(self._ctx, k, int(expected_distinct), part, n_parts))
+
+    def kc_add(self, bases: np.ndarray, seq_off: np.ndarray, parent: int):
+        bases = _arr(bases, np.uint8).reshape(-1)
+        seq_off = _arr(seq_off, np.uint32)
+        t = C.c_uint64()
+        self._ck(self.lib.hast_kc_add(self._ctx, _ptr(bases), bases.size, _ptr(seq_off), seq_off.size - 1, parent,
+                                      C.byref(t)))
+        self._ck(self.lib.hast_wait_copied(self._ctx, t.value))
+
+    def kc_add_device(self, bases_ptr: int, n_bases: int, off_ptr: int, n_seqs: int, parent: int):
+        self._ck(self.lib.hast_kc_add_device(self._ctx, bases_ptr, n_bases, off_ptr, n_seqs, parent))
+
+    def kc_info(self) -> KcInfo:
+        ki = KcInfo()
+        self._ck(self.lib.hast_kc_info_get(self._ctx, C.byref(ki)))
+        return ki
+
+    def kc_histo(self, parent: int, high: int = 10000) -> np.ndarray:
+        h = np.zeros(high + 2, np.uint64)
+        self._ck(self.lib.hast_kc_histo(self._ctx, parent, high, _ptr(h)))
+        return h
+
+    def kc_select(self, parent: int, lower: int, upper: int, require_unique: bool = True) -> np.ndarray:
+        """Sorted canonical k-mers in jellyfish's code (A0 C1 G2 T3)."""
+        n = C.c_uint64()
+        self._ck(self.lib.hast_kc_select(self._ctx, parent, lower, upper, int(require_unique), None, 0, C.byref(n)))
+        out = np.zeros(max(1, n.value), np.uint64)
+        self._ck(self.lib.hast_kc_select(self._ctx, parent, lower, upper, int(require_unique), _ptr(out), n.value,
+                                         C.byref(n)))
+        return out[:n.value]
+
+    def kc_to_table(self, pl: int, pu: int, ml: int, mu: int, dst: "Engine | None" = None):
+        self._ck(self.lib.hast_kc_to_table((dst or self)._ctx, self._ctx, pl, pu, ml, mu))
+
+    def kc_end(self):
+        self._ck(self.lib.hast_kc_end(self._ctx))
+
+
+def kmers_to_text(kmers: np.ndarray, k: int, letters: bytes = b"ACGT") -> bytes:
+    """Packed k-mers (first base in the highest used bits) -> one k-mer per line.  letters = b"ACGT" for
+    jellyfish's code (hast_kc_select), b"ACTG" for kmer.h's."""
+    lut = np.frombuffer(letters, np.uint8)
+    km = np.ascontiguousarray(kmers, np.uint64)
+    out = np.empty((km.size, k + 1), np.uint8)
+    for j in range(k):
+        out[:, j] = lut[((km >> np.uint64(2 * (k - 1 - j))) & np.uint64(3)).astype(np.intp)]
+    out[:, k] = ord("\n")
+    return out.tobytes()

@@ -19,6 +19,8 @@
 
 #include "kernels.cuh"
 #include "fused.cuh"
+#include "kcount.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 using namespace hast;
 
@@ -114,6 +116,10 @@ struct hast_ctx {
     int64_t opt_seq_mode = 0;             // 1 = stage-03 window rule (classify_kernel<.., SEQ>)
     int64_t opt_filter_bits_per_key = 16;
     int64_t opt_filter_max_bytes = (int64_t)64 << 20;
+    // stage 00 (kcount.cuh)
+    KcView kc{};
+    uint64_t kc_slots = 0;
+    KcStats* d_kc_stats = nullptr;
     std::string err;
 };
 
@@ -287,6 +293,8 @@ void hast_destroy(hast_ctx* ctx) {
     cudaFree(ctx->d_reduced);
     cudaFree(ctx->d_stats);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->kc.slots);
+    cudaFree(ctx->d_kc_stats);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->cs) cudaStreamDestroy(ctx->cs);
@@ -869,6 +877,279 @@ int hast_gather_roofline(hast_ctx* ctx, uint64_t n_probes, uint64_t span_bytes, 
     ctx->st.kernel_launches += 2;
     *gbps = ms > 0 ? (float)((double)n_probes * 32.0 / (ms * 1e-3) / 1e9) : 0.f;
     return HAST_OK;
+}
+
+// ---- stage 00: k-mer counting (kcount.cuh) -------------------------------------
+static int kc_ready(hast_ctx* ctx) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (!ctx->kc.slots) return fail(ctx, HAST_E_STATE, "hast_kc_begin first");
+    return HAST_OK;
+}
+
+int hast_kc_end(hast_ctx* ctx) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->hs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    if (ctx->kc.slots) { CU(cudaFree(ctx->kc.slots)); ctx->kc.slots = nullptr; }
+    ctx->kc_slots = 0;
+    return HAST_OK;
+}
+
+int hast_kc_begin(hast_ctx* ctx, int k, uint64_t expected_distinct, uint32_t part, uint32_t n_parts) {
+    if (!ctx) return fail(nullptr, HAST_E_ARG, "NULL context");
+    if (k < 1 || k > 32) return fail(ctx, HAST_E_K, "k must be in 1..32");
+    if (n_parts < 1 || part >= n_parts) return fail(ctx, HAST_E_ARG, "need part < n_parts");
+    int rc = hast_kc_end(ctx);
+    if (rc) return rc;
+    int b = 10;
+    while (((uint64_t)1 << b) < 2 * expected_distinct && b < 36) ++b;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (((uint64_t)16 << b) > free_b)
+        return fail(ctx, HAST_E_TABLE_FULL, "count table of " + std::to_string(((uint64_t)16 << b) >> 20) +
+                    " MiB does not fit the free device memory: use more partitions");
+    ctx->kc_slots = (uint64_t)1 << b;
+    CU(cudaMalloc(&ctx->kc.slots, ctx->kc_slots * sizeof(KcSlot)));
+    CU(cudaMemsetAsync(ctx->kc.slots, 0, ctx->kc_slots * sizeof(KcSlot), ctx->cs));
+    if (!ctx->d_kc_stats) CU(cudaMalloc(&ctx->d_kc_stats, sizeof(KcStats)));
+    CU(cudaMemsetAsync(ctx->d_kc_stats, 0, sizeof(KcStats), ctx->cs));
+    ctx->kc.mask = ctx->kc_slots - 1;
+    ctx->kc.k = k;
+    ctx->kc.part = part;
+    ctx->kc.n_parts = n_parts;
+    ctx->kc.max_probe = (uint32_t)std::min<uint64_t>(ctx->kc_slots, 8192);
+    return HAST_OK;
+}
+
+static int kc_launch(hast_ctx* ctx, const BatchView& bv, int parent) {
+    const uint32_t n_tiles = (bv.n_reads + kKcReadsPerTile - 1) / kKcReadsPerTile;
+    if (!n_tiles) return HAST_OK;
+    const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 4);
+    switch (ctx->kc.k) {
+        case 21: kc_count_kernel<21><<<grid, kTileThreads, sizeof(KcSmem), ctx->cs>>>(ctx->kc, bv, (uint32_t)parent, ctx->d_kc_stats); break;
+        case 31: kc_count_kernel<31><<<grid, kTileThreads, sizeof(KcSmem), ctx->cs>>>(ctx->kc, bv, (uint32_t)parent, ctx->d_kc_stats); break;
+        default: kc_count_kernel<0><<<grid, kTileThreads, sizeof(KcSmem), ctx->cs>>>(ctx->kc, bv, (uint32_t)parent, ctx->d_kc_stats); break;
+    }
+    CU(cudaGetLastError());
+    ctx->st.kernel_launches++;
+    return HAST_OK;
+}
+
+int hast_kc_add_device(hast_ctx* ctx, const uint8_t* d_bases, uint64_t n_bases, const uint32_t* d_seq_off,
+                       uint32_t n_seqs, int parent) {
+    int rc = kc_ready(ctx);
+    if (rc) return rc;
+    if (parent < 0 || parent > 1) return fail(ctx, HAST_E_ARG, "parent must be 0 or 1");
+    if (!n_seqs) return HAST_OK;
+    if (!d_bases || !d_seq_off) return fail(ctx, HAST_E_ARG, "NULL batch array");
+    if ((uintptr_t)d_bases & 15) return fail(ctx, HAST_E_ARG, "d_bases must be 16-byte aligned");
+    if (n_bases >= 0xFFFFFFF0ull) return fail(ctx, HAST_E_ARG, "batch larger than 4 GiB of bases");
+    CU(cudaSetDevice(ctx->device));
+    BatchView bv{d_bases, d_seq_off, nullptr, n_bases, n_seqs, nullptr, nullptr};
+    return kc_launch(ctx, bv, parent);
+}
+
+int hast_kc_add(hast_ctx* ctx, const uint8_t* bases, uint64_t n_bases, const uint32_t* seq_off, uint32_t n_seqs,
+                int parent, uint64_t* ticket) {
+    int rc = kc_ready(ctx);
+    if (rc) return rc;
+    if (parent < 0 || parent > 1) return fail(ctx, HAST_E_ARG, "parent must be 0 or 1");
+    if (ticket) *ticket = ctx->seq;
+    if (!n_seqs) return HAST_OK;
+    if (!seq_off || (!bases && n_bases)) return fail(ctx, HAST_E_ARG, "NULL batch array");
+    if (n_bases >= 0xFFFFFFF0ull) return fail(ctx, HAST_E_ARG, "batch larger than 4 GiB of bases");
+    CU(cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[ctx->seq % kSlots];
+    CU(cudaEventSynchronize(s.done));
+    if ((rc = ensure(ctx, (void**)&s.d_bases, &s.cap_bases, n_bases + 16))) return rc;
+    if ((rc = ensure(ctx, (void**)&s.d_off, &s.cap_off, ((size_t)n_seqs + 1) * 4))) return rc;
+    CU(cudaMemcpyAsync(s.d_bases, bases, n_bases, cudaMemcpyHostToDevice, ctx->hs));
+    CU(cudaMemcpyAsync(s.d_off, seq_off, ((size_t)n_seqs + 1) * 4, cudaMemcpyHostToDevice, ctx->hs));
+    CU(cudaEventRecord(s.copied, ctx->hs));
+    CU(cudaStreamWaitEvent(ctx->cs, s.copied, 0));
+    BatchView bv{s.d_bases, s.d_off, nullptr, n_bases, n_seqs, nullptr, nullptr};
+    if ((rc = kc_launch(ctx, bv, parent))) return rc;
+    CU(cudaEventRecord(s.done, ctx->cs));
+    ctx->st.h2d_bytes += n_bases + ((size_t)n_seqs + 1) * 4;
+    ctx->st.batches++;
+    ctx->st.reads += n_seqs;
+    ctx->st.bases += n_bases;
+    ctx->seq++;
+    return HAST_OK;
+}
+
+static int kc_read_stats(hast_ctx* ctx, KcStats* ks) {
+    CU(cudaStreamSynchronize(ctx->hs));
+    CU(cudaMemcpyAsync(ks, ctx->d_kc_stats, sizeof(KcStats), cudaMemcpyDeviceToHost, ctx->cs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    if (ks->too_long)
+        return fail(ctx, HAST_E_ARG, std::to_string(ks->too_long) + " sequence chunk(s) longer than " +
+                    std::to_string(kKcCap - 16) + " bytes: cut them with k-1 bytes of overlap");
+    return HAST_OK;
+}
+
+int hast_kc_info_get(hast_ctx* ctx, hast_kc_info* out) {
+    int rc = kc_ready(ctx);
+    if (rc) return rc;
+    if (!out) return fail(ctx, HAST_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    KcStats ks;
+    if ((rc = kc_read_stats(ctx, &ks))) return rc;
+    if ((rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, sizeof(KcTotals)))) return rc;
+    CU(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(KcTotals), ctx->cs));
+    kc_totals_kernel<<<grid_for(ctx, ctx->kc_slots, 256), 256, 0, ctx->cs>>>(ctx->kc.slots, ctx->kc_slots,
+                                                                          (KcTotals*)ctx->d_scratch);
+    CU(cudaGetLastError());
+    ctx->st.kernel_launches++;
+    KcTotals t;
+    CU(cudaMemcpyAsync(&t, ctx->d_scratch, sizeof(t), cudaMemcpyDeviceToHost, ctx->cs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    out->k = ctx->kc.k;
+    out->part = ctx->kc.part;
+    out->n_parts = ctx->kc.n_parts;
+    out->n_slots = ctx->kc_slots;
+    out->bytes = ctx->kc_slots * sizeof(KcSlot);
+    out->occupied = t.occupied;
+    out->distinct[0] = t.distinct[0];
+    out->distinct[1] = t.distinct[1];
+    out->both = t.both;
+    out->occurrences[0] = t.occurrences[0];
+    out->occurrences[1] = t.occurrences[1];
+    out->windows = ks.windows;
+    out->table_full = ks.table_full;
+    return HAST_OK;
+}
+
+static int kc_check_full(hast_ctx* ctx) {
+    KcStats ks;
+    int rc = kc_read_stats(ctx, &ks);
+    if (rc) return rc;
+    if (ks.table_full)
+        return fail(ctx, HAST_E_TABLE_FULL, std::to_string(ks.table_full) +
+                    " k-mer occurrence(s) found no slot in the count table: use a larger expected_distinct or more partitions");
+    return HAST_OK;
+}
+
+int hast_kc_histo(hast_ctx* ctx, int parent, uint32_t high, uint64_t* histo) {
+    int rc = kc_ready(ctx);
+    if (rc) return rc;
+    if (parent < 0 || parent > 1 || !histo || high < 1 || high > (1u << 24)) return fail(ctx, HAST_E_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = kc_check_full(ctx))) return rc;
+    const size_t bytes = ((size_t)high + 2) * 8;
+    if ((rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, bytes))) return rc;
+    CU(cudaMemsetAsync(ctx->d_scratch, 0, bytes, ctx->cs));
+    kc_histo_kernel<<<grid_for(ctx, ctx->kc_slots, 256, 4), 256, 0, ctx->cs>>>(
+        ctx->kc.slots, ctx->kc_slots, (uint32_t)parent, high, (unsigned long long*)ctx->d_scratch);
+    CU(cudaGetLastError());
+    ctx->st.kernel_launches++;
+    CU(cudaMemcpyAsync(histo, ctx->d_scratch, bytes, cudaMemcpyDeviceToHost, ctx->cs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    return HAST_OK;
+}
+
+// selection of one parent into d_scratch: [counter (16 B)] [keys, cap of them] ; sorted when `sort`
+static int kc_select_device(hast_ctx* ctx, int parent, uint32_t lower, uint32_t upper, bool require_unique,
+                            bool hast_code, bool sort, uint64_t** d_keys, uint64_t* n_out) {
+    int rc;
+    // pass 1: how many
+    if ((rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, 16))) return rc;
+    CU(cudaMemsetAsync(ctx->d_scratch, 0, 16, ctx->cs));
+    const int grid = grid_for(ctx, ctx->kc_slots, 256, 8);
+    kc_select_kernel<<<grid, 256, 0, ctx->cs>>>(ctx->kc.slots, ctx->kc_slots, (uint32_t)parent, lower, upper,
+                                                require_unique, hast_code, nullptr, 0,
+                                                (unsigned long long*)ctx->d_scratch);
+    CU(cudaGetLastError());
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, ctx->d_scratch, 8, cudaMemcpyDeviceToHost, ctx->cs));
+    CU(cudaStreamSynchronize(ctx->cs));
+    ctx->st.kernel_launches++;
+    *n_out = n;
+    *d_keys = nullptr;
+    if (!n) return HAST_OK;
+    size_t tmp_bytes = 0;
+    if (sort) cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (size_t)n,
+                                             0, 2 * ctx->kc.k, ctx->cs);
+    const size_t o_a = 16, o_b = o_a + n * 8, o_tmp = (o_b + (sort ? n * 8 : 0) + 255) & ~(size_t)255;
+    if ((rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, o_tmp + tmp_bytes))) return rc;
+    char* d = (char*)ctx->d_scratch;
+    CU(cudaMemsetAsync(d, 0, 16, ctx->cs));
+    kc_select_kernel<<<grid, 256, 0, ctx->cs>>>(ctx->kc.slots, ctx->kc_slots, (uint32_t)parent, lower, upper,
+                                                require_unique, hast_code, (uint64_t*)(d + o_a), n,
+                                                (unsigned long long*)d);
+    CU(cudaGetLastError());
+    ctx->st.kernel_launches++;
+    if (sort) {
+        CU(cub::DeviceRadixSort::SortKeys(d + o_tmp, tmp_bytes, (const uint64_t*)(d + o_a), (uint64_t*)(d + o_b), (size_t)n,
+                                          0, 2 * ctx->kc.k, ctx->cs));
+        *d_keys = (uint64_t*)(d + o_b);
+    } else {
+        *d_keys = (uint64_t*)(d + o_a);
+    }
+    return HAST_OK;
+}
+
+int hast_kc_select(hast_ctx* ctx, int parent, uint32_t lower, uint32_t upper, int require_unique, uint64_t* out,
+                   uint64_t cap, uint64_t* n) {
+    int rc = kc_ready(ctx);
+    if (rc) return rc;
+    if (parent < 0 || parent > 1 || !n || (cap && !out)) return fail(ctx, HAST_E_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = kc_check_full(ctx))) return rc;
+    uint64_t* d_keys = nullptr;
+    if ((rc = kc_select_device(ctx, parent, lower, upper, require_unique != 0, false, true, &d_keys, n))) return rc;
+    const uint64_t m = std::min(*n, cap);
+    if (m) {
+        CU(cudaMemcpyAsync(out, d_keys, m * 8, cudaMemcpyDeviceToHost, ctx->cs));
+        CU(cudaStreamSynchronize(ctx->cs));
+        ctx->st.d2h_bytes += m * 8;
+    }
+    return HAST_OK;
+}
+
+int hast_kc_to_table(hast_ctx* dst, hast_ctx* src, uint32_t pl, uint32_t pu, uint32_t ml, uint32_t mu) {
+    hast_ctx* ctx = src;
+    int rc = kc_ready(src);
+    if (rc) return rc;
+    if (!dst) return fail(src, HAST_E_ARG, "NULL context");
+    if (dst->device != src->device) return fail(src, HAST_E_ARG, "dst and src must be on the same device (clone the table afterwards)");
+    if (src->kc.n_parts != 1) return fail(src, HAST_E_STATE, "the count table holds one partition only");
+    CU(cudaSetDevice(src->device));
+    if ((rc = kc_check_full(src))) return rc;
+    // sizes first (the table is sized from them), then one selection + insertion per parent
+    uint64_t n[2] = {0, 0};
+    uint64_t* d_keys = nullptr;
+    const uint32_t lo[2] = {pl, ml}, hi[2] = {pu, mu};
+    for (int p = 0; p < 2; ++p) {
+        if ((rc = ensure(src, &src->d_scratch, &src->cap_scratch, 16))) return rc;
+        CU(cudaMemsetAsync(src->d_scratch, 0, 16, src->cs));
+        kc_select_kernel<<<grid_for(src, src->kc_slots, 256, 8), 256, 0, src->cs>>>(
+            src->kc.slots, src->kc_slots, (uint32_t)p, lo[p], hi[p], true, true, nullptr, 0,
+            (unsigned long long*)src->d_scratch);
+        CU(cudaGetLastError());
+        unsigned long long c = 0;
+        CU(cudaMemcpyAsync(&c, src->d_scratch, 8, cudaMemcpyDeviceToHost, src->cs));
+        CU(cudaStreamSynchronize(src->cs));
+        src->st.kernel_launches++;
+        n[p] = c;
+    }
+    if ((rc = hast_table_begin(dst, src->kc.k, std::max<uint64_t>(n[0] + n[1], 16)))) {
+        if (dst != src) src->err = dst->err;
+        return rc;
+    }
+    for (int p = 0; p < 2; ++p) {
+        uint64_t m = 0;
+        if ((rc = kc_select_device(src, p, lo[p], hi[p], true, true, false, &d_keys, &m))) return rc;
+        if (!m) continue;
+        CU(cudaStreamSynchronize(src->cs));
+        table_insert_packed_kernel<<<grid_for(dst, m, 256), 256, 0, dst->cs>>>(dst->tv, d_keys, m, (uint32_t)p, dst->d_stats);
+        CU(cudaGetLastError());
+        dst->st.kernel_launches++;
+        CU(cudaStreamSynchronize(dst->cs));
+    }
+    ctx = dst;
+    return table_check(dst);
 }
 
 }  // extern "C"

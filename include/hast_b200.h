@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HAST_ABI_VERSION 2
+#define HAST_ABI_VERSION 3
 
 #define HAST_OK            0
 #define HAST_E_ARG        -1   /* bad argument                                            */
@@ -198,6 +198,55 @@ int hast_lookup_device(hast_ctx *ctx, const uint64_t *d_canonical, uint64_t n, u
  * random-access roofline the lookup kernel is compared with.  Returns the
  * achieved GB/s of n_probes independent sector reads.                         */
 int hast_gather_roofline(hast_ctx *ctx, uint64_t n_probes, uint64_t span_bytes, float *gbps);
+
+/* ---- stage 00: parent-unique k-mer lists from parental reads ------------ */
+/* Replaces 00.build_unshare_kmers_by_jellyfish/build_unshared_kmers.sh:163-291 (five
+ * `jellyfish count -m K -C` runs, the dumps between them and the "2 copies of maternal +
+ * 1 copy of paternal" mix, :262-291) by one device table of per-parent counts.
+ * K-mers cross this part of the ABI in jellyfish's code (A0 C1 G2 T3, first base in the
+ * highest used bits), canonical = the numerically smaller of a k-mer and its reverse
+ * complement = the string `jellyfish dump` prints.                                    */
+typedef struct hast_kc_info {
+    int32_t  k;
+    uint32_t part, n_parts;   /* this table keeps the keys of partition `part` of `n_parts` */
+    uint64_t n_slots;         /* 16-byte slots                                          */
+    uint64_t bytes;
+    uint64_t occupied;        /* distinct canonical k-mers stored (either parent)       */
+    uint64_t distinct[2];     /* ... seen in the paternal / maternal reads              */
+    uint64_t both;            /* ... seen in both                                       */
+    uint64_t occurrences[2];  /* sum of counts per parent                               */
+    uint64_t windows;         /* valid k-mer windows streamed past (all partitions)     */
+    uint64_t table_full;      /* insertions that found no slot: rebuild larger / more partitions */
+} hast_kc_info;
+/* begin: k in 1..32; the table gets the smallest power-of-two number of slots >= 2 *
+ * expected_distinct (load <= 0.5).  n_parts > 1: only canonical k-mers whose partition
+ * (top bits of a 64-bit mix) equals `part` are counted, the others are skipped -- stream
+ * the same reads once per partition, or to several GPUs that each own one.            */
+int hast_kc_begin(hast_ctx *ctx, int k, uint64_t expected_distinct, uint32_t part, uint32_t n_parts);
+/* `jellyfish count -C` over one batch of sequences of parent `parent` (0 paternal,
+ * 1 maternal): sequence i is bases[seq_off[i] .. seq_off[i+1]) (ASCII; a sequence line of a
+ * FASTQ record or the joined lines of a FASTA record).  A sequence longer than 32768 bytes
+ * must be cut by the caller into chunks that overlap by k-1 bytes.  Every window of k
+ * bytes all in ACGTacgt counts once.  Host form: asynchronous, see hast_wait_copied.   */
+int hast_kc_add(hast_ctx *ctx, const uint8_t *bases, uint64_t n_bases, const uint32_t *seq_off,
+                uint32_t n_seqs, int parent, uint64_t *ticket);
+int hast_kc_add_device(hast_ctx *ctx, const uint8_t *d_bases, uint64_t n_bases, const uint32_t *d_seq_off,
+                       uint32_t n_seqs, int parent);
+int hast_kc_info_get(hast_ctx *ctx, hast_kc_info *out);
+/* `jellyfish histo -h high` of one parent (analysis_kmercount.sh:7-9): histo[c] = number
+ * of distinct k-mers with count c for 1 <= c <= high, histo[high+1] = those above,
+ * histo[0] = all distinct k-mers of the parent.  histo holds high + 2 entries.        */
+int hast_kc_histo(hast_ctx *ctx, int parent, uint32_t high, uint64_t *histo);
+/* The k-mers of `parent` with lower <= count <= upper (`jellyfish dump -L -U`), and, when
+ * require_unique, absent from the other parent (build_unshared_kmers.sh:262-291), sorted
+ * ascending, up to cap of them into out; *n receives how many there are.              */
+int hast_kc_select(hast_ctx *ctx, int parent, uint32_t lower, uint32_t upper, int require_unique,
+                   uint64_t *out, uint64_t cap, uint64_t *n);
+/* Build the classification table of stage 01 (hast_table_begin + both parents' lists)
+ * straight from the count table of `src`, on the device, without the text round trip;
+ * bounds as in the script: paternal [pl,pu], maternal [ml,mu].  dst may equal src.     */
+int hast_kc_to_table(hast_ctx *dst, hast_ctx *src, uint32_t pl, uint32_t pu, uint32_t ml, uint32_t mu);
+int hast_kc_end(hast_ctx *ctx);
 
 #ifdef __cplusplus
 }
