@@ -30,10 +30,10 @@ $(TOOLS): hast_b200/tools/fastq_fmt.c
 	@mkdir -p hast_b200/lib
 	$(CC) -O2 -std=c11 -fPIC -shared $< -lz -o $@
 
-host: bin/classify bin/mergeResult bin/quartering_fastq bin/classify_seq bin/build_unshared_kmers
+host: bin/classify bin/mergeResult bin/quartering_fastq bin/classify_seq bin/build_unshared_kmers bin/hast_gunzip
 HOST_SRCS := $(wildcard $(HOST)/*.cpp)
 HOST_HDRS := $(wildcard $(HOST)/*.h)
-MAINS := $(HOST)/merge_result_main.cpp $(HOST)/quartering_main.cpp $(HOST)/classify_main.cpp $(HOST)/classify_seq_main.cpp $(HOST)/build_unshared_main.cpp
+MAINS := $(HOST)/merge_result_main.cpp $(HOST)/quartering_main.cpp $(HOST)/classify_main.cpp $(HOST)/classify_seq_main.cpp $(HOST)/build_unshared_main.cpp $(HOST)/gunzip_main.cpp
 bin/classify: $(filter-out $(MAINS),$(HOST_SRCS)) $(HOST)/classify_main.cpp $(HOST_HDRS) $(LIB) include/hast_b200.h
 	@mkdir -p bin
 	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(filter-out $(MAINS),$(HOST_SRCS)) $(HOST)/classify_main.cpp \
@@ -44,14 +44,18 @@ bin/classify_seq: $(HOST)/classify_seq_main.cpp $(LIB) include/hast_b200.h
 	$(CXX) -O2 -g -std=c++17 -Wall -Iinclude $(HOST)/classify_seq_main.cpp -Lhast_b200/lib -lhast_b200 -lz \
 	    -Wl,-rpath,'$$ORIGIN/../hast_b200/lib' -o $@
 # stage 00's parent-unique k-mer lists from parental reads (count table on the GPU)
-bin/build_unshared_kmers: $(HOST)/build_unshared_main.cpp $(LIB) include/hast_b200.h
+bin/build_unshared_kmers: $(HOST)/build_unshared_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate.h $(LIB) include/hast_b200.h
 	@mkdir -p bin
-	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(HOST)/build_unshared_main.cpp -Lhast_b200/lib -lhast_b200 -lz \
+	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(HOST)/build_unshared_main.cpp $(HOST)/inflate.cpp -Lhast_b200/lib -lhast_b200 -lz \
 	    -Wl,-rpath,'$$ORIGIN/../hast_b200/lib' -o $@
 # the read partitioner alone needs no GPU and no CUDA library
 bin/quartering_fastq: $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/fastq_source.cpp $(HOST_HDRS)
 	@mkdir -p bin
-	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/fastq_source.cpp -lz -o $@
+	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/fastq_source.cpp $(HOST)/inflate.cpp -lz -o $@
+# the gzip decoder of the readers as a stand-alone tool (tests, timing)
+bin/hast_gunzip: $(HOST)/gunzip_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate.h
+	@mkdir -p bin
+	$(CXX) -O2 -g -std=c++17 -Wall $(HOST)/gunzip_main.cpp $(HOST)/inflate.cpp -lz -o $@
 bin/mergeResult: $(HOST)/merge_result_main.cpp
 	@mkdir -p bin
 	$(CXX) -O2 -g -std=c++17 -Wall $< -o $@

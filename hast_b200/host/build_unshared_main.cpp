@@ -33,12 +33,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/hast_b200.h"
+#include "inflate.h"
 
 namespace {
 
@@ -124,9 +126,14 @@ public:
         : k_(k), chunk_(chunk), free_(free_q), full_(full_q), parent_(parent) {}
 
     std::string run(const std::string& path) {
-        gzFile gz = gzopen(path.c_str(), "rb");            // passes plain text through
-        if (!gz) return "cannot open " + path;
-        gzbuffer(gz, 1u << 20);
+        std::unique_ptr<hasthost::GzipInflater> inf(new hasthost::GzipInflater());
+        if (!inf->open(path).empty() || !inf->is_gzip() || getenv("HAST_ZLIB")) inf.reset();
+        gzFile gz = nullptr;
+        if (!inf) {
+            gz = gzopen(path.c_str(), "rb");               // passes plain text through
+            if (!gz) return "cannot open " + path;
+            gzbuffer(gz, 1u << 20);
+        }
         std::vector<char> buf(4u << 20);
         std::string line;
         enum { kStart, kFastaSeq, kFqSeq, kFqQual } st = kStart;
@@ -154,13 +161,9 @@ public:
                     return;
             }
         };
-        for (;;) {
-            const int r = gzread(gz, buf.data(), (unsigned)buf.size());
-            if (r < 0) { int e = 0; std::string m = gzerror(gz, &e); gzclose(gz); return "gzread failed on " + path + ": " + m; }
-            if (r == 0) break;
-            text_bytes_ += (uint64_t)r;
-            const char* p = buf.data();
-            const char* const end = p + r;
+        auto feed = [&](const char* p, size_t n) {
+            text_bytes_ += (uint64_t)n;
+            const char* const end = p + n;
             while (p < end) {
                 const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
                 if (!nl) { line.append(p, (size_t)(end - p)); break; }
@@ -168,10 +171,22 @@ public:
                 else { line.append(p, (size_t)(nl - p)); handle(line.data(), line.size()); line.clear(); }
                 p = nl + 1;
             }
+        };
+        if (inf) {                                         // gzip members: the readers' own decoder (inflate.h)
+            const uint8_t* p;
+            size_t n;
+            while (inf->next(&p, &n)) feed((const char*)p, n);
+            if (!inf->error().empty()) return "inflate failed on " + path + ": " + inf->error();
+        } else
+        for (;;) {
+            const int r = gzread(gz, buf.data(), (unsigned)buf.size());
+            if (r < 0) { int e = 0; std::string m = gzerror(gz, &e); gzclose(gz); return "gzread failed on " + path + ": " + m; }
+            if (r == 0) break;
+            feed(buf.data(), (size_t)r);
         }
         if (!line.empty()) handle(line.data(), line.size());
         if (st == kFastaSeq || st == kFqSeq) end_seq();
-        gzclose(gz);
+        if (gz) gzclose(gz);
         (void)fastq;
         flush();
         return "";

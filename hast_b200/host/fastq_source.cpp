@@ -6,6 +6,7 @@
 #include <unistd.h>
 
 #include <cerrno>
+#include <cstdlib>
 #include <cstring>
 
 namespace hasthost {
@@ -34,6 +35,14 @@ std::string FastqSource::open(const std::string& path) {
         fd_ = dup(STDIN_FILENO);
         if (fd_ < 0) return std::string("cannot read standard input: ") + strerror(errno);
     } else if (gz) {
+        const char* force = getenv("HAST_ZLIB");
+        if (!(force && force[0] == '1')) {
+            std::unique_ptr<GzipInflater> inf(new GzipInflater());
+            if (inf->open(path).empty() && inf->is_gzip()) {
+                inf_ = std::move(inf);
+                return "";
+            }
+        }
         gz_ = gzopen(path.c_str(), "rb");
         if (!gz_) return "cannot open " + path;
         gzbuffer(gz_, 1u << 20);
@@ -48,6 +57,24 @@ std::string FastqSource::open(const std::string& path) {
 }
 
 size_t FastqSource::raw_read(char* dst, size_t n, std::string& err) {
+    if (inf_) {
+        size_t got = 0;
+        while (got < n) {
+            if (!chunk_left_) {
+                if (!inf_->next(&chunk_, &chunk_left_)) {
+                    if (!inf_->error().empty()) { err = "inflate failed on " + path_ + ": " + inf_->error(); return 0; }
+                    break;
+                }
+            }
+            const size_t m = std::min(n - got, chunk_left_);
+            memcpy(dst + got, chunk_, m);
+            got += m;
+            chunk_ += m;
+            chunk_left_ -= m;
+            if (got >= (1u << 20)) break;              // hand back what one call of read() would: whole chunks, not the whole block
+        }
+        return got;
+    }
     if (gz_) {
         const unsigned want = (unsigned)std::min<size_t>(n, 1u << 30);
         const int r = gzread(gz_, dst, want);

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "host.h"
+#include "inflate.h"
 
 namespace hasthost {
 
@@ -13,8 +14,9 @@ namespace hasthost {
 // vendored gzstream (gzstream.C:78-101, 299-byte gzread calls): large reads /
 // inflates into recycled buffers, cut so that every block holds whole four-line
 // records.  ".gz" is decided by the file-name suffix alone (classify.cpp:245-250);
-// zlib's gzread also walks concatenated gzip members and passes plain text
-// through, exactly like the reference's igzstream.
+// gzip members are decoded by GzipInflater (inflate.h; concatenated members walked like
+// zlib's gzread does); a ".gz" file that holds plain text is passed through by zlib's
+// gzread, exactly like the reference's igzstream.  HAST_ZLIB=1 forces zlib for gzip too.
 class FastqSource {
 public:
     FastqSource() = default;
@@ -30,6 +32,9 @@ private:
     size_t raw_read(char* dst, size_t n, std::string& err);
     std::string path_;
     gzFile gz_ = nullptr;
+    std::unique_ptr<GzipInflater> inf_;
+    const uint8_t* chunk_ = nullptr;   // unread part of the inflater's current chunk
+    size_t chunk_left_ = 0;
     int fd_ = -1;
     bool eof_ = false;
     std::vector<char> carry_;      // bytes after the last record boundary handed out
