@@ -38,7 +38,7 @@ public:
     uint64_t bytes_out() const { return total_out_; }
 
     static constexpr size_t kWindow = 32768;
-    static constexpr size_t kChunk = 4u << 20;
+    static constexpr size_t kChunk = 1u << 20;
 
 private:
     enum class Phase { kHeader, kBlockHeader, kStored, kHuffman, kTrailer, kDone, kError };

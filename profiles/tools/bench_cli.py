@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""End-to-end throughput of the drop-in PROCESS (bin/classify: open files, inflate, parse, intern barcodes,
+H2D, classify, reduce, print the table) next to the untouched reference binary on the same files.
+
+    python profiles/tools/bench_cli.py [--pairs 4000000] [--gpus 1] > out.json
+
+Workload: the configs[1] trio (100 Mbp, k=21) with the first `pairs` read pairs written as child.r1/r2 FASTQ,
+plain and gzip (level 6, `gzip -6`: what sequencers ship).  Legs: plain / gz through the readers' own decoder /
+gz through zlib (HAST_ZLIB=1) / the reference binary (oracle/_ref/classify_O2, best --thread) on the gz files.
+Reported per leg: wall seconds of the whole process and pairs/s; for bin/classify also the streaming phase alone
+(--stats-json).  Output tables are compared byte for byte.
+"""
+import argparse
+import gzip
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pairs", type=int, default=4_000_000)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-reference", action="store_true")
+    args = ap.parse_args()
+    from hast_b200 import synth
+    import torch
+    cores = os.cpu_count() or 8
+    threads = args.threads or max(4, cores - 4)
+    spec = synth.config("cfg2")
+    spec.n_pairs = args.pairs
+    spec.n_barcodes = max(1000, args.pairs // 40)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    t0 = time.perf_counter()
+    trio = synth.make_trio(spec, device=dev)
+    print(f"[cli] trio in {time.perf_counter() - t0:.1f}s", file=sys.stderr)
+    out = {"pairs": args.pairs, "host_cores": cores, "parser_threads": threads, "gpus": args.gpus, "legs": {}}
+    with tempfile.TemporaryDirectory(prefix="hast_cli_", dir=os.environ.get("TMPDIR", "/tmp")) as d:
+        d = Path(d)
+        pat, mat = trio.write_kmer_lists(d)
+        r1, r2 = trio.write_fastq(d, gz=False)
+        gz = []
+        for p in (r1, r2):                                     # gzip -6 like a sequencer's output
+            subprocess.run(["gzip", "-6", "-k", p], check=True)
+            gz.append(p + ".gz")
+        out["fastq_bytes"] = os.path.getsize(r1) + os.path.getsize(r2)
+        out["gz_bytes"] = sum(os.path.getsize(p) for p in gz)
+        exe = str(ROOT / "bin" / "classify")
+
+        def run_ours(name, reads, env_extra):
+            stats = d / f"{name}.json"
+            cmd = [exe, "--hap0", pat, "--hap1", mat, "--weight0", "1.04", "--thread", str(threads), "--gpus", str(args.gpus),
+                   "--stats-json", str(stats)]
+            for r in reads:
+                cmd += ["--read", r]
+            best = None
+            for _ in range(2):
+                t = time.perf_counter()
+                r = subprocess.run(cmd, capture_output=True, env=dict(os.environ, **env_extra))
+                dt = time.perf_counter() - t
+                assert r.returncode == 0, r.stderr[-500:]
+                st = json.loads(stats.read_text())
+                if best is None or dt < best[0]:
+                    best = (dt, st, r.stdout)
+            dt, st, table = best
+            out["legs"][name] = {"wall_s": dt, "pairs_per_s": args.pairs / dt, "stream_s": st["t_reads_s"],
+                                 "pairs_per_s_stream": st["pairs_per_s_stream"], "t_table_s": st["t_table_s"],
+                                 "text_MBps_stream": st["fastq_text_bytes"] / st["t_reads_s"] / 1e6}
+            return table
+
+        t_plain = run_ours("plain", [r1, r2], {})
+        t_gz = run_ours("gz", gz, {})
+        t_zlib = run_ours("gz_zlib", gz, {"HAST_ZLIB": "1"})
+        assert t_plain == t_gz == t_zlib
+        out["tables_identical"] = True
+        ref = ROOT / "oracle" / "_ref" / "classify_O2"
+        if ref.exists() and not args.no_reference:
+            best = None
+            for t in sorted({8, 16, min(32, cores)}):
+                cmd = [str(ref), "--hap0", pat, "--hap1", mat, "--weight0", "1.04", "--thread", str(t), "--read", gz[0], "--read", gz[1]]
+                s = time.perf_counter()
+                r = subprocess.run(cmd, capture_output=True)
+                dt = time.perf_counter() - s
+                assert r.returncode == 0
+                if best is None or dt < best[0]:
+                    best = (dt, t, r.stdout)
+            dt, t, table = best
+            out["legs"]["reference_gz"] = {"wall_s": dt, "pairs_per_s": args.pairs / dt, "threads": t,
+                                           "binary": "oracle/_ref/classify_O2 (untouched reference sources, -O2)"}
+            out["reference_table_identical"] = table == t_gz
+            assert table == t_gz, "reference table differs"
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

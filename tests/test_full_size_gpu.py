@@ -62,6 +62,7 @@ def _run(e, job, sub, order=None):
             b = d_bases.view(n, L)[idx].contiguous()
             c = d_bc[idx].contiguous()
             keep += [b, c]
+            torch.cuda.synchronize()           # torch gathers on its own stream; the engine launches on another
             e.submit_batch_device(b.data_ptr(), m * L, d_off.data_ptr(), c.data_ptr(), m)
             e.sync()
             keep.clear()
@@ -75,7 +76,7 @@ def test_full_size_properties(job):
     whole, lookups = _run(e, job, 4_000_000)
     assert whole.sum() > 1_000_000 and lookups > 3_000_000_000
     # linearity under a different, ragged split
-    parts, lookups2 = _run(e, job, 1_234_567)
+    parts, lookups2 = _run(e, job, 1_234_568)      # ragged, but a multiple of 4 reads: device batches start 16-byte aligned
     assert (parts == whole).all() and lookups2 == lookups
     # permutation invariance
     g = torch.Generator(device="cuda:0")
