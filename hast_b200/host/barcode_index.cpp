@@ -2,9 +2,14 @@
 //
 // The reference keys a std::map<std::string, ...> by the barcode text
 // (classify.cpp:50-56) and creates the entry for every read, scoring or not
-// (:191,208).  Here the text -> id map lives on the host (sharded open
-// addressing under per-shard locks, so all parser threads can intern at once)
-// and only the dense id travels to the device.
+// (:191,208).  Here the text -> id map lives on the host and only the dense id
+// travels to the device.  Interning runs once per read on every parser thread,
+// so the common case -- a barcode seen before -- takes no lock: every shard
+// publishes an immutable-size open-addressing table through an atomic pointer,
+// entries become visible by a release store of their hash, strings live in
+// chunks that never move, and a table that fills up is replaced by a larger
+// copy while the old one stays alive for the readers still probing it (they
+// can only miss, and a miss re-probes the current table under the shard lock).
 #include <cstring>
 #include <mutex>
 
@@ -28,62 +33,125 @@ inline uint64_t hash_bytes(const char* s, size_t n) {
     h ^= h >> 29;
     h *= 0xff51afd7ed558ccdull;
     h ^= h >> 32;
-    return h;
+    return h ? h : 1;                 // 0 marks an empty slot
 }
-struct Entry { uint64_t hash; uint64_t off; uint32_t len; uint32_t id; };
+// 32 bytes, two per cache line: a lookup of a typical stLFR barcode ("1234_567_89": <= 16 bytes, kept inline)
+// touches one line; longer names live in the shard's arena.
+struct Entry {
+    std::atomic<uint64_t> hash{0};   // written last (release): the other fields are complete when it is non-zero
+    uint32_t id = 0;
+    uint32_t len = 0;
+    union { char text[16]; const char* ptr; } u{};
+    const char* data() const { return len <= sizeof(u.text) ? u.text : u.ptr; }
+};
+static_assert(sizeof(Entry) == 32, "two entries per cache line");
+struct Table {
+    explicit Table(size_t n) : mask(n - 1), slots(new Entry[n]) {}
+    size_t mask;
+    std::unique_ptr<Entry[]> slots;
+};
+constexpr size_t kArenaChunk = 1u << 16;
 }  // namespace
 
 struct BarcodeIndex::Shard {
+    std::atomic<Table*> cur{nullptr};
     std::mutex mu;
-    std::vector<Entry> tab;          // power-of-two open addressing; len == UINT32_MAX marks empty
-    std::vector<char> arena;
+    std::vector<std::unique_ptr<Table>> tables;          // every generation stays alive
+    std::vector<std::unique_ptr<char[]>> chunks;         // strings never move
+    size_t chunk_used = kArenaChunk;
     size_t used = 0;
     char pad[64];
 
-    Shard() { tab.assign(1024, Entry{0, 0, UINT32_MAX, 0}); }
-    void grow() {
-        std::vector<Entry> old;
-        old.swap(tab);
-        tab.assign(old.size() * 2, Entry{0, 0, UINT32_MAX, 0});
-        const size_t m = tab.size() - 1;
-        for (const Entry& e : old) {
-            if (e.len == UINT32_MAX) continue;
-            size_t i = (size_t)(e.hash >> 8) & m;
-            while (tab[i].len != UINT32_MAX) i = (i + 1) & m;
-            tab[i] = e;
+    Shard() {
+        tables.emplace_back(new Table(1024));
+        cur.store(tables.back().get(), std::memory_order_release);
+    }
+    const char* store(const char* s, size_t n) {
+        if (n > kArenaChunk / 4) {                       // an oversized name gets a chunk of its own
+            chunks.emplace_back(new char[n]);
+            memcpy(chunks.back().get(), s, n);
+            const char* p = chunks.back().get();
+            chunk_used = kArenaChunk;                    // next small string opens a fresh chunk
+            return p;
         }
+        if (chunk_used + n > kArenaChunk) { chunks.emplace_back(new char[kArenaChunk]); chunk_used = 0; }
+        char* p = chunks.back().get() + chunk_used;
+        memcpy(p, s, n);
+        chunk_used += n;
+        return p;
+    }
+    void grow() {
+        Table* old = cur.load(std::memory_order_relaxed);
+        std::unique_ptr<Table> nt(new Table((old->mask + 1) * 2));
+        for (size_t i = 0; i <= old->mask; ++i) {
+            const Entry& e = old->slots[i];
+            const uint64_t h = e.hash.load(std::memory_order_relaxed);
+            if (!h) continue;
+            size_t j = (size_t)(h >> 8) & nt->mask;
+            while (nt->slots[j].hash.load(std::memory_order_relaxed)) j = (j + 1) & nt->mask;
+            nt->slots[j].u = e.u;
+            nt->slots[j].len = e.len;
+            nt->slots[j].id = e.id;
+            nt->slots[j].hash.store(h, std::memory_order_relaxed);
+        }
+        tables.push_back(std::move(nt));
+        cur.store(tables.back().get(), std::memory_order_release);
     }
 };
 
 BarcodeIndex::BarcodeIndex() : shards_(new Shard[kShards]) {}
 BarcodeIndex::~BarcodeIndex() = default;
 
-uint32_t BarcodeIndex::intern(const char* s, size_t n) {
-    const uint64_t h = hash_bytes(s, n);
+uint64_t BarcodeIndex::hash(const char* s, size_t n) { return hash_bytes(s, n); }
+
+void BarcodeIndex::prefetch(uint64_t h) const {
+    const Table* t = shards_[h & (kShards - 1)].cur.load(std::memory_order_acquire);
+    __builtin_prefetch(&t->slots[(size_t)(h >> 8) & t->mask]);
+}
+
+uint32_t BarcodeIndex::intern(const char* s, size_t n) { return intern_hashed(hash_bytes(s, n), s, n); }
+
+uint32_t BarcodeIndex::intern_hashed(uint64_t h, const char* s, size_t n) {
     Shard& sh = shards_[h & (kShards - 1)];
+    {                                                    // lock-free: seen before
+        const Table* t = sh.cur.load(std::memory_order_acquire);
+        size_t i = (size_t)(h >> 8) & t->mask;
+        for (;;) {
+            const Entry& e = t->slots[i];
+            const uint64_t eh = e.hash.load(std::memory_order_acquire);
+            if (!eh) break;
+            if (eh == h && e.len == n && memcmp(e.data(), s, n) == 0) return e.id;
+            i = (i + 1) & t->mask;
+        }
+    }
     std::lock_guard<std::mutex> lk(sh.mu);
-    size_t m = sh.tab.size() - 1;
-    size_t i = (size_t)(h >> 8) & m;
+    Table* t = sh.cur.load(std::memory_order_relaxed);
+    size_t i = (size_t)(h >> 8) & t->mask;
     for (;;) {
-        Entry& e = sh.tab[i];
-        if (e.len == UINT32_MAX) break;
-        if (e.hash == h && e.len == n && memcmp(sh.arena.data() + e.off, s, n) == 0) return e.id;
-        i = (i + 1) & m;
+        Entry& e = t->slots[i];
+        const uint64_t eh = e.hash.load(std::memory_order_relaxed);
+        if (!eh) break;
+        if (eh == h && e.len == n && memcmp(e.data(), s, n) == 0) return e.id;
+        i = (i + 1) & t->mask;
     }
     const uint32_t id = next_id_.fetch_add(1, std::memory_order_acq_rel);
-    const uint64_t off = sh.arena.size();
-    sh.arena.insert(sh.arena.end(), s, s + n);
-    sh.tab[i] = Entry{h, off, (uint32_t)n, id};
-    if (++sh.used * 2 > sh.tab.size()) sh.grow();
+    Entry& e = t->slots[i];
+    if (n <= sizeof(e.u.text)) memcpy(e.u.text, s, n); else e.u.ptr = sh.store(s, n);
+    e.len = (uint32_t)n;
+    e.id = id;
+    e.hash.store(h, std::memory_order_release);
+    if (++sh.used * 2 > t->mask + 1) sh.grow();
     return id;
 }
 
 void BarcodeIndex::export_names(std::vector<std::string>& out) const {
     out.assign(size(), std::string());
     for (int s = 0; s < kShards; ++s) {
-        const Shard& sh = shards_[s];
-        for (const Entry& e : sh.tab)
-            if (e.len != UINT32_MAX) out[e.id].assign(sh.arena.data() + e.off, e.len);
+        const Table* t = shards_[s].cur.load(std::memory_order_acquire);
+        for (size_t i = 0; i <= t->mask; ++i) {
+            const Entry& e = t->slots[i];
+            if (e.hash.load(std::memory_order_acquire)) out[e.id].assign(e.data(), e.len);
+        }
     }
 }
 

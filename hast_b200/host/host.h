@@ -55,6 +55,11 @@ public:
     BarcodeIndex();
     ~BarcodeIndex();
     uint32_t intern(const char* s, size_t n);
+    // the same in two steps, so that a parser can have the table line of record i+8 on its way while it
+    // resolves record i (the table of a 20 M-barcode run is far larger than the caches)
+    static uint64_t hash(const char* s, size_t n);
+    void prefetch(uint64_t h) const;
+    uint32_t intern_hashed(uint64_t h, const char* s, size_t n);
     uint32_t size() const { return next_id_.load(std::memory_order_acquire); }
     // names in id order (call after all parsing finished)
     void export_names(std::vector<std::string>& out) const;

@@ -8,6 +8,7 @@
 // then dies on in chopRead2Kmer, kmer.h:171; here the device flags it and
 // hast_finish fails).
 #include <cstring>
+#include <immintrin.h>
 
 #include "host.h"
 
@@ -22,9 +23,33 @@ static inline bool any_N4_host(uint32_t w) {
     return ((x - 0x01010101u) & ~x & 0x80808080u) != 0u;
 }
 
+// 16 bases per step with SSSE3: codes = (byte >> 1) & 3, pmaddubsw folds base pairs (x4 + y), pmaddwd folds
+// the pairs of pairs (x16 + y), a byte shuffle lines the four 8-bit groups up first-base-on-top.
+__attribute__((target("ssse3"))) static size_t pack_run_ssse3(const char* seq, size_t n, uint32_t* words, size_t& n_words,
+                                                              uint64_t& acc, unsigned& nbits, bool& has_n) {
+    const __m128i three = _mm_set1_epi8(3), w1 = _mm_set1_epi16(0x0104), w2 = _mm_set1_epi32(0x00010010);
+    const __m128i gather = _mm_set_epi8(-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 4, 8, 12);
+    const __m128i big_n = _mm_set1_epi8('N');
+    __m128i any_n = _mm_setzero_si128();
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(seq + i));
+        any_n = _mm_or_si128(any_n, _mm_cmpeq_epi8(v, big_n));
+        const __m128i codes = _mm_and_si128(_mm_srli_epi16(v, 1), three);
+        const __m128i quads = _mm_madd_epi16(_mm_maddubs_epi16(codes, w1), w2);
+        const uint32_t w = (uint32_t)_mm_cvtsi128_si32(_mm_shuffle_epi8(quads, gather));
+        acc = (acc << 32) | w;
+        words[n_words++] = (uint32_t)(acc >> nbits);     // nbits < 32 pending bits stay pending
+    }
+    if (_mm_movemask_epi8(any_n)) has_n = true;
+    return i;
+}
+
 bool pack_append(const char* seq, size_t n, uint32_t* words, size_t& n_words, uint64_t& acc, unsigned& nbits) {
     bool has_n = false;
     size_t i = 0;
+    static const bool have_ssse3 = __builtin_cpu_supports("ssse3");
+    if (have_ssse3 && n >= 16) i = pack_run_ssse3(seq, n, words, n_words, acc, nbits, has_n);
     for (; i + 4 <= n; i += 4) {
         uint32_t w;
         memcpy(&w, seq + i, 4);
@@ -56,6 +81,15 @@ bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out) {
     out.error.clear();
     uint32_t n = 0;
     uint64_t nb = 0;
+    // barcode interning runs kRing records behind the framing, with the table line prefetched in between
+    constexpr uint32_t kRing = 8;
+    struct Pending { const char* s; size_t len; uint64_t h; } ring[kRing];
+    auto resolve = [&](uint32_t r) {
+        const Pending& q = ring[r % kRing];
+        const uint32_t id = index.intern_hashed(q.h, q.s, q.len);
+        if (id > out.max_barcode) out.max_barcode = id;
+        out.barcode_id[r] = id;
+    };
     while (p < end) {
         const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
         if (!nl) break;                                   // unterminated header at EOF: dropped
@@ -73,8 +107,12 @@ bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out) {
         }
         size_t bs, bl;
         parse_name(head, hlen, bs, bl);                   // classify.cpp:112-119
-        const uint32_t id = index.intern(head + bs, bl);
-        if (id > out.max_barcode) out.max_barcode = id;
+        if (n >= kRing) resolve(n - kRing);
+        Pending& q = ring[n % kRing];
+        q.s = head + bs;
+        q.len = bl;
+        q.h = BarcodeIndex::hash(q.s, q.len);
+        index.prefetch(q.h);
         if (packed) {
             if ((n & 31u) == 0) out.has_n[n >> 5] = 0;
             if (pack_append(seq, slen, out.packed, n_words, acc, nbits)) out.has_n[n >> 5] |= 1u << (n & 31u);
@@ -82,7 +120,6 @@ bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out) {
             memcpy(out.bases + nb, seq, slen);
         }
         out.read_off[n] = (uint32_t)nb;
-        out.barcode_id[n] = id;
         nb += slen;
         ++n;
         for (int i = 0; i < 2 && p < end; ++i) {          // '+' line and quality line
@@ -90,6 +127,7 @@ bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out) {
             p = nl ? nl + 1 : end;
         }
     }
+    for (uint32_t r = n >= kRing ? n - kRing : 0; r < n; ++r) resolve(r);
     if (packed && nbits) out.packed[n_words++] = (uint32_t)(acc << (32 - nbits));   // zero-padded last word
     out.read_off[n] = (uint32_t)nb;
     out.n_reads = n;
