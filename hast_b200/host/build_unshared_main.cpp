@@ -41,6 +41,7 @@
 
 #include "../../include/hast_b200.h"
 #include "inflate.h"
+#include "inflate_par.h"
 
 namespace {
 
@@ -122,14 +123,19 @@ private:
 // dropped); a FASTQ record's sequence runs until the '+' line and its quality until it is as long.
 class SeqReader {
 public:
-    SeqReader(int k, size_t chunk, Queue<SeqBatch*>& free_q, Queue<SeqBatch*>& full_q, int parent)
-        : k_(k), chunk_(chunk), free_(free_q), full_(full_q), parent_(parent) {}
+    SeqReader(int k, size_t chunk, Queue<SeqBatch*>& free_q, Queue<SeqBatch*>& full_q, int parent, int inflate_threads)
+        : k_(k), chunk_(chunk), free_(free_q), full_(full_q), parent_(parent), inflate_threads_(inflate_threads) {}
 
     std::string run(const std::string& path) {
         std::unique_ptr<hasthost::GzipInflater> inf(new hasthost::GzipInflater());
         if (!inf->open(path).empty() || !inf->is_gzip() || getenv("HAST_ZLIB")) inf.reset();
+        std::unique_ptr<hasthost::ParallelGzip> pinf;
+        if (inf && inflate_threads_ > 1) {                 // one gzip stream on several threads (inflate_par.h)
+            pinf.reset(new hasthost::ParallelGzip(inflate_threads_));
+            if (!pinf->open(path).empty()) pinf.reset(); else inf.reset();
+        }
         gzFile gz = nullptr;
-        if (!inf) {
+        if (!inf && !pinf) {
             gz = gzopen(path.c_str(), "rb");               // passes plain text through
             if (!gz) return "cannot open " + path;
             gzbuffer(gz, 1u << 20);
@@ -172,7 +178,12 @@ public:
                 p = nl + 1;
             }
         };
-        if (inf) {                                         // gzip members: the readers' own decoder (inflate.h)
+        if (pinf) {
+            const uint8_t* p;
+            size_t n;
+            while (pinf->next(&p, &n)) feed((const char*)p, n);
+            if (!pinf->error().empty()) return "inflate failed on " + path + ": " + pinf->error();
+        } else if (inf) {                                  // gzip members: the readers' own decoder (inflate.h)
             const uint8_t* p;
             size_t n;
             while (inf->next(&p, &n)) feed((const char*)p, n);
@@ -249,6 +260,7 @@ private:
     Queue<SeqBatch*>& free_;
     Queue<SeqBatch*>& full_;
     int parent_;
+    int inflate_threads_;
     SeqBatch* cur_ = nullptr;
     size_t piece_ = 0;
     bool in_seq_ = false;
@@ -471,12 +483,14 @@ int main(int argc, char** argv) {
                 std::vector<std::thread> readers;
                 q_full.reopen();
                 const int n_readers = left;
+                int inflate_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2u / (unsigned)std::max(n_readers, 1)));
+                if (const char* e = getenv("HAST_INFLATE_THREADS")) inflate_threads = std::max(1, atoi(e));
                 for (int r = 0; r < n_readers; ++r)
                     readers.emplace_back([&] {
                         for (;;) {
                             const size_t i = next.fetch_add(1);
                             if (i >= files.size()) break;
-                            SeqReader rd(k, kChunk, q_free, q_full, files[i].second);
+                            SeqReader rd(k, kChunk, q_free, q_full, files[i].second, inflate_threads);
                             const std::string e = rd.run(files[i].first);
                             std::lock_guard<std::mutex> lk(err_mu);
                             if (!e.empty() && err.empty()) err = e;

@@ -27,7 +27,7 @@ FastqSource::~FastqSource() {
     if (fd_ >= 0) close(fd_);
 }
 
-std::string FastqSource::open(const std::string& path) {
+std::string FastqSource::open(const std::string& path, int inflate_threads) {
     path_ = path;
     const size_t n = path.size();
     const bool gz = n > 3 && path[n - 3] == '.' && path[n - 2] == 'g' && path[n - 1] == 'z';   // classify.cpp:245-250
@@ -36,6 +36,13 @@ std::string FastqSource::open(const std::string& path) {
         if (fd_ < 0) return std::string("cannot read standard input: ") + strerror(errno);
     } else if (gz) {
         const char* force = getenv("HAST_ZLIB");
+        if (!(force && force[0] == '1') && inflate_threads > 1) {
+            std::unique_ptr<ParallelGzip> pinf(new ParallelGzip(inflate_threads));
+            if (pinf->open(path).empty() && pinf->is_gzip()) {
+                pinf_ = std::move(pinf);
+                return "";
+            }
+        }
         if (!(force && force[0] == '1')) {
             std::unique_ptr<GzipInflater> inf(new GzipInflater());
             if (inf->open(path).empty() && inf->is_gzip()) {
@@ -57,12 +64,14 @@ std::string FastqSource::open(const std::string& path) {
 }
 
 size_t FastqSource::raw_read(char* dst, size_t n, std::string& err) {
-    if (inf_) {
+    if (inf_ || pinf_) {
         size_t got = 0;
         while (got < n) {
             if (!chunk_left_) {
-                if (!inf_->next(&chunk_, &chunk_left_)) {
-                    if (!inf_->error().empty()) { err = "inflate failed on " + path_ + ": " + inf_->error(); return 0; }
+                const bool more = inf_ ? inf_->next(&chunk_, &chunk_left_) : pinf_->next(&chunk_, &chunk_left_);
+                if (!more) {
+                    const std::string& e = inf_ ? inf_->error() : pinf_->error();
+                    if (!e.empty()) { err = "inflate failed on " + path_ + ": " + e; return 0; }
                     break;
                 }
             }

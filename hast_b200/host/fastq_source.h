@@ -7,6 +7,7 @@
 
 #include "host.h"
 #include "inflate.h"
+#include "inflate_par.h"
 
 namespace hasthost {
 
@@ -22,7 +23,8 @@ public:
     FastqSource() = default;
     ~FastqSource();
     // returns "" or an error message
-    std::string open(const std::string& path);
+    // inflate_threads > 1: a gzip file is decoded by ParallelGzip (inflate_par.h) on that many threads
+    std::string open(const std::string& path, int inflate_threads = 1);
     // Fills blk with the next run of whole records (blk.len > 0) and returns true;
     // returns false at end of file.  The block that ends the file has last_of_file set
     // and may end in a partial record / unterminated line.  err is set on I/O failure.
@@ -33,6 +35,7 @@ private:
     std::string path_;
     gzFile gz_ = nullptr;
     std::unique_ptr<GzipInflater> inf_;
+    std::unique_ptr<ParallelGzip> pinf_;
     const uint8_t* chunk_ = nullptr;   // unread part of the inflater's current chunk
     size_t chunk_left_ = 0;
     int fd_ = -1;

@@ -4,21 +4,27 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "inflate.h"
+#include "inflate_par.h"
 
 int main(int argc, char** argv) {
     bool null_out = false, use_zlib = false;
+    int threads = 1;
+    size_t chunk = 1u << 20;
     std::string path;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--null")) null_out = true;
         else if (!strcmp(argv[i], "--zlib")) use_zlib = true;
+        else if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--chunk") && i + 1 < argc) chunk = (size_t)atol(argv[++i]);
         else path = argv[i];
     }
-    if (path.empty()) { fputs("usage: hast_gunzip [--null] [--zlib] FILE.gz\n", stderr); return 2; }
+    if (path.empty()) { fputs("usage: hast_gunzip [--null] [--zlib] [--threads N [--chunk BYTES]] FILE.gz\n", stderr); return 2; }
     const auto t0 = std::chrono::steady_clock::now();
     unsigned long long total = 0;
     if (use_zlib) {
@@ -34,6 +40,21 @@ int main(int argc, char** argv) {
             if (!null_out) fwrite(buf.data(), 1, (size_t)r, stdout);
         }
         gzclose(gz);
+    } else if (threads > 1) {
+        hasthost::ParallelGzip inf(threads, chunk);
+        const std::string e = inf.open(path);
+        if (!e.empty()) { fprintf(stderr, "%s\n", e.c_str()); return 1; }
+        const uint8_t* p;
+        size_t n;
+        while (inf.next(&p, &n)) {
+            total += n;
+            if (!null_out) fwrite(p, 1, n, stdout);
+        }
+        if (!inf.error().empty()) { fflush(stdout); fprintf(stderr, "error: %s\n", inf.error().c_str()); return 1; }
+        const auto st = inf.stats();
+        fprintf(stderr, "parallel: %llu chunks in %llu batches, %llu block starts found, %llu dropped\n",
+                (unsigned long long)st.chunks, (unsigned long long)st.batches, (unsigned long long)st.starts_found,
+                (unsigned long long)st.starts_dropped);
     } else {
         hasthost::GzipInflater inf;
         const std::string e = inf.open(path);

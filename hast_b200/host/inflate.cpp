@@ -27,8 +27,8 @@ namespace {
 constexpr uint32_t kKindMask = 3u << 6;
 constexpr uint32_t kLit = 0u << 6, kBase = 1u << 6, kEob = 2u << 6, kSub = 3u << 6;
 constexpr uint32_t kInvalid = kEob | (0xFFFFu << 16) | 1u;     // drops one bit, flagged invalid
-constexpr int kLitlenRoot = 11, kDistRoot = 8;
-constexpr size_t kLitlenCap = 4096, kDistCap = 1024;
+constexpr int kLitlenRoot = GzipInflater::kLitlenRoot, kDistRoot = GzipInflater::kDistRoot;
+constexpr size_t kLitlenCap = GzipInflater::kLitlenCap, kDistCap = GzipInflater::kDistCap;
 constexpr size_t kTail = 64;                                   // private, zero-padded copy of the last input bytes
 constexpr size_t kSlack = 258 + 64;                            // a match may run past the chunk limit
 
@@ -180,7 +180,8 @@ bool GzipInflater::parse_trailer() {
     return true;
 }
 
-bool GzipInflater::build_table(const uint8_t* lens, int n, int root, uint32_t* table, size_t cap, bool litlen) {
+bool GzipInflater::build_table(const uint8_t* lens, int n, int root, uint32_t* table, size_t cap, bool litlen,
+                               bool pack_literals) {
     uint16_t count[16] = {0};
     for (int i = 0; i < n; ++i) count[lens[i]]++;
     count[0] = 0;
@@ -252,7 +253,7 @@ bool GzipInflater::build_table(const uint8_t* lens, int n, int root, uint32_t* t
         }
     }
     static const bool no_pack = getenv("HAST_NOPACK") != nullptr;
-    if (litlen && !no_pack) {
+    if (litlen && pack_literals && !no_pack) {
         // pack the literals that follow a short literal code into its root entries
         uint32_t single[1 << kLitlenRoot];
         memcpy(single, table, root_size * sizeof(uint32_t));
@@ -281,10 +282,10 @@ void GzipInflater::build_fixed() {
     for (int i = 144; i < 256; ++i) lens[i] = 9;
     for (int i = 256; i < 280; ++i) lens[i] = 7;
     for (int i = 280; i < 288; ++i) lens[i] = 8;
-    build_table(lens, 288, kLitlenRoot, fixed_litlen_.data(), kLitlenCap, true);
+    build_table(lens, 288, kLitlenRoot, fixed_litlen_.data(), kLitlenCap, true, true);
     uint8_t d[32];
     for (int i = 0; i < 32; ++i) d[i] = 5;
-    build_table(d, 32, kDistRoot, fixed_dist_.data(), kDistCap, false);
+    build_table(d, 32, kDistRoot, fixed_dist_.data(), kDistCap, false, false);
     fixed_built_ = true;
 }
 
@@ -339,8 +340,8 @@ bool GzipInflater::build_dynamic() {
     }
     if (input_overrun()) return fail("unexpected end of file");
     if (lens[256] == 0) return fail("invalid code -- missing end-of-block");
-    if (!build_table(lens, hlit, kLitlenRoot, litlen_.data(), kLitlenCap, true)) return fail("invalid literal/lengths set");
-    if (!build_table(lens + hlit, hdist, kDistRoot, dist_.data(), kDistCap, false)) return fail("invalid distances set");
+    if (!build_table(lens, hlit, kLitlenRoot, litlen_.data(), kLitlenCap, true, true)) return fail("invalid literal/lengths set");
+    if (!build_table(lens + hlit, hdist, kDistRoot, dist_.data(), kDistCap, false, false)) return fail("invalid distances set");
     cur_litlen_ = litlen_.data();
     cur_dist_ = dist_.data();
     return true;

@@ -38,6 +38,13 @@ public:
     uint64_t bytes_out() const { return total_out_; }
 
     static constexpr size_t kWindow = 32768;
+    // Two-level decode table of one canonical Huffman code (entry layout: inflate.cpp).  `pack_literals`: root
+    // entries of short literal codes also carry the one or two literals that follow.  Shared with the
+    // parallel decoder (inflate_par.cpp).  Returns false for an over-subscribed or incomplete code.
+    static constexpr int kLitlenRoot = 11, kDistRoot = 8;
+    static constexpr size_t kLitlenCap = 4096, kDistCap = 1024;
+    static bool build_table(const uint8_t* lens, int n, int root_bits, uint32_t* table, size_t cap, bool litlen,
+                            bool pack_literals);
     static constexpr size_t kChunk = 1u << 20;
 
 private:
@@ -48,7 +55,6 @@ private:
     bool read_block_header();
     bool build_dynamic();
     void build_fixed();
-    bool build_table(const uint8_t* lens, int n, int root_bits, uint32_t* table, size_t cap, bool litlen);
     bool decode_huffman(uint8_t*& out, uint8_t* out_limit);
     void remap_tail();
     void refill();

@@ -244,6 +244,9 @@ int run_classify(const Options& opt, RunStats& st) {
     std::atomic<uint64_t> text_bytes{0};
     std::atomic<size_t> next_file{0};
     const int n_readers = (int)std::max<size_t>(1, std::min<size_t>({opt.reads.size(), (size_t)opt.threads, (size_t)8}));
+    // threads per gzip stream (inflate_par.h): half the cores go to inflating, shared by the files read at once
+    int inflate_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2u / (unsigned)n_readers));
+    if (const char* e = getenv("HAST_INFLATE_THREADS")) inflate_threads = std::max(1, atoi(e));
     std::atomic<int> readers_left{n_readers};
     std::vector<std::thread> readers;
     for (int r = 0; r < n_readers; ++r)
@@ -254,7 +257,7 @@ int run_classify(const Options& opt, RunStats& st) {
                 const std::string& path = opt.reads[fi];
                 fprintf(stderr, "__process read: %s\n", path.c_str());
                 FastqSource src;
-                std::string e = src.open(path);
+                std::string e = src.open(path, inflate_threads);
                 if (!e.empty()) { sh.fail(e); abort_all(); break; }
                 bool stop = false;
                 for (;;) {

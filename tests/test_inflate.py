@@ -16,8 +16,13 @@ ROOT = Path(__file__).resolve().parent.parent
 TOOL = ROOT / "bin" / "hast_gunzip"
 
 
-def gunzip(path):
-    return subprocess.run([str(TOOL), str(path)], capture_output=True)
+MODES = {"serial": [], "parallel": ["--threads", "3", "--chunk", "40000"], "parallel_big_chunks": ["--threads", "2", "--chunk", "700000"]}
+
+
+def gunzip(path, mode="serial"):
+    """serial = GzipInflater; parallel = ParallelGzip (inflate_par.cpp) with chunks small enough that even the small
+    test streams are cut dozens of times."""
+    return subprocess.run([str(TOOL)] + MODES[mode] + [str(path)], capture_output=True)
 
 
 def gz_member(data: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, wbits=15, memlevel=8, fname=None, comment=None,
@@ -70,15 +75,18 @@ def test_tool_built():
     assert TOOL.exists(), "bin/hast_gunzip missing: make host"
 
 
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("level", [0, 1, 4, 6, 9])
 @pytest.mark.parametrize("name", ["fastq", "random", "zeros", "period3", "tiny", "empty", "text", "skewed", "wide"])
-def test_matches_zlib(tmp_path, payloads, name, level):
+def test_matches_zlib(tmp_path, payloads, name, level, mode):
     data = payloads[name]
     p = tmp_path / "x.gz"
     p.write_bytes(gzip.compress(data, compresslevel=level))
-    r = gunzip(p)
+    r = gunzip(p, mode)
     assert r.returncode == 0, r.stderr
     assert r.stdout == data
+    if mode == "parallel" and name in ("fastq", "skewed") and level > 0:       # these compress to many 40 kB chunks
+        assert b"block starts found" in r.stderr and int(r.stderr.split(b" block starts found")[0].split()[-1]) > 3, r.stderr
 
 
 @pytest.mark.parametrize("strategy", [zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED])
@@ -89,9 +97,10 @@ def test_strategies_and_windows(tmp_path, payloads, strategy, wbits, memlevel):
         data = payloads[name][:1_500_000]
         p = tmp_path / "x.gz"
         p.write_bytes(gz_member(data, 6, strategy, wbits, memlevel))
-        r = gunzip(p)
-        assert r.returncode == 0, r.stderr
-        assert r.stdout == data, (name, strategy)
+        for mode in ("serial", "parallel"):
+            r = gunzip(p, mode)
+            assert r.returncode == 0, r.stderr
+            assert r.stdout == data, (name, strategy, mode)
 
 
 def test_members_headers_and_trailing_garbage(tmp_path, payloads):
@@ -99,13 +108,14 @@ def test_members_headers_and_trailing_garbage(tmp_path, payloads):
     blob = (gz_member(a, fname=b"reads.fq", comment=b"made by hand", extra=b"BC\x02\x00\x10\x00", hcrc=True) +
             gz_member(b"") + gz_member(b, level=1) + gz_member(c, level=9, fname=b"x"))
     p = tmp_path / "multi.gz"
-    p.write_bytes(blob)
-    r = gunzip(p)
-    assert r.returncode == 0 and r.stdout == a + b + c
-    # zlib's gzread ignores whatever follows the last member; so do we
-    p.write_bytes(blob + b"\0" * 700 + b"trailing junk")
-    r = gunzip(p)
-    assert r.returncode == 0 and r.stdout == a + b + c
+    for mode in MODES:
+        p.write_bytes(blob)
+        r = gunzip(p, mode)
+        assert r.returncode == 0 and r.stdout == a + b + c, mode
+        # zlib's gzread ignores whatever follows the last member; so do we
+        p.write_bytes(blob + b"\0" * 700 + b"trailing junk")
+        r = gunzip(p, mode)
+        assert r.returncode == 0 and r.stdout == a + b + c, mode
     assert gzip.decompress(blob) == a + b + c
 
 
@@ -114,11 +124,13 @@ def test_many_small_members_like_bgzip(tmp_path, payloads):
     blob = b"".join(gz_member(data[i:i + 60_000], extra=b"BC\x02\x00\xff\xff") for i in range(0, len(data), 60_000))
     p = tmp_path / "blocks.gz"
     p.write_bytes(blob)
-    r = gunzip(p)
-    assert r.returncode == 0 and r.stdout == data
+    for mode in MODES:
+        r = gunzip(p, mode)
+        assert r.returncode == 0 and r.stdout == data, mode
 
 
-def test_truncated_and_corrupted_input_is_an_error_not_a_crash(tmp_path, payloads):
+@pytest.mark.parametrize("mode", ["serial", "parallel"])
+def test_truncated_and_corrupted_input_is_an_error_not_a_crash(tmp_path, payloads, mode):
     data = payloads["fastq"][:400_000]
     blob = gzip.compress(data, compresslevel=6)
     p = tmp_path / "bad.gz"
@@ -127,7 +139,7 @@ def test_truncated_and_corrupted_input_is_an_error_not_a_crash(tmp_path, payload
                       rng.integers(12, len(blob) - 9, 40).tolist()))
     for cut in cuts:
         p.write_bytes(blob[:cut])
-        r = gunzip(p)
+        r = gunzip(p, mode)
         assert r.returncode == 1 and b"error" in r.stderr, (cut, r.returncode, r.stderr[-200:])
         assert data.startswith(r.stdout)                           # whatever came out before the error is right
     # flipped bits: either the stream breaks or a check (CRC-32 / length) catches it; wrong data never passes
@@ -135,7 +147,7 @@ def test_truncated_and_corrupted_input_is_an_error_not_a_crash(tmp_path, payload
         bad = bytearray(blob)
         bad[pos] ^= 1 << int(rng.integers(0, 8))
         p.write_bytes(bytes(bad))
-        r = gunzip(p)
+        r = gunzip(p, mode)
         if r.returncode == 0:
             assert r.stdout == data, pos                           # a flip in dead bits (e.g. header MTIME) changes nothing
         else:
@@ -145,13 +157,14 @@ def test_truncated_and_corrupted_input_is_an_error_not_a_crash(tmp_path, payload
         bad = bytearray(blob)
         bad[len(blob) - off] ^= 0x55
         p.write_bytes(bytes(bad))
-        r = gunzip(p)
+        r = gunzip(p, mode)
         assert r.returncode == 1 and b"incorrect" in r.stderr
     p.write_bytes(b"plain text, not gzip\n")
-    assert gunzip(p).returncode == 1
+    assert gunzip(p, mode).returncode == 1
 
 
-def test_hand_made_invalid_streams(tmp_path):
+@pytest.mark.parametrize("mode", ["serial", "parallel"])
+def test_hand_made_invalid_streams(tmp_path, mode):
     head = bytes([0x1F, 0x8B, 8, 0, 0, 0, 0, 0, 0, 255])
     p = tmp_path / "bad.gz"
     cases = {
@@ -161,12 +174,12 @@ def test_hand_made_invalid_streams(tmp_path):
     }
     for name, body in cases.items():
         p.write_bytes(head + body + bytes(16))
-        r = gunzip(p)
+        r = gunzip(p, mode)
         assert r.returncode == 1, name
     p.write_bytes(bytes([0x1F, 0x8B, 7, 0, 0, 0, 0, 0, 0, 255]) + bytes(20))
-    assert gunzip(p).returncode == 1                               # unknown compression method
+    assert gunzip(p, mode).returncode == 1                               # unknown compression method
     p.write_bytes(bytes([0x1F, 0x8B, 8, 0x80, 0, 0, 0, 0, 0, 255]) + bytes(20))
-    assert gunzip(p).returncode == 1                               # reserved flag bits
+    assert gunzip(p, mode).returncode == 1                               # reserved flag bits
 
 
 def test_readers_use_it_and_agree_with_zlib(tmp_path, payloads):
@@ -178,9 +191,24 @@ def test_readers_use_it_and_agree_with_zlib(tmp_path, payloads):
     fq.write_bytes(gzip.compress(payloads["fastq"], compresslevel=6))
     (tmp_path / "k.mer").write_bytes(b"ACGTACGTACGTACGTACGTA\n")
     outs = []
-    for force in ("0", "1"):
+    for force, threads in (("0", "1"), ("1", "1"), ("0", "3")):
         r = subprocess.run([str(exe), "-p", str(tmp_path / "k.mer"), "-m", str(tmp_path / "k.mer"), "-r", str(fq), "-t", "3"],
-                           capture_output=True, env=dict(os.environ, HAST_PARSE_ONLY="1", HAST_ZLIB=force))
+                           capture_output=True, env=dict(os.environ, HAST_PARSE_ONLY="1", HAST_ZLIB=force, HAST_INFLATE_THREADS=threads))
         assert r.returncode == 0, r.stderr[-300:]
         outs.append(r.stdout)
-    assert outs[0] == outs[1] and len(outs[0]) > 100_000
+    assert outs[0] == outs[1] == outs[2] and len(outs[0]) > 100_000
+
+
+def test_false_block_starts_are_dropped(tmp_path, payloads):
+    """A gzip file stored inside stored blocks: the block finder sees perfectly valid dynamic-Huffman headers followed by
+    text, but they are payload bytes of the outer stream.  The chunk before each of them runs past it on no block
+    boundary, so the candidate is dropped and the output is still exact."""
+    inner = gzip.compress(payloads["fastq"][:6_000_000], compresslevel=6)
+    p = tmp_path / "nested.gz"
+    p.write_bytes(gzip.compress(inner, compresslevel=0))
+    r = gunzip(p, "parallel")
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == inner
+    dropped = int(r.stderr.split(b" dropped")[0].split()[-1])
+    found = int(r.stderr.split(b" block starts found")[0].split()[-1])
+    assert found > 3 and dropped == found, r.stderr
