@@ -344,10 +344,20 @@ void decode_chunk(const uint8_t* in, size_t n, ParallelGzip::Chunk& c, const std
                 r.refill();
                 uint32_t e;
                 HASTP_LOOKUP(e, lt, kLitlenRoot, r);
-                if ((e & kKindMask) == kLit) {
+                if ((e & kKindMask) == kLit) {             // up to three literals out of one refill (56 bits)
                     *out++ = (uint16_t)((e >> 8) & 0xFFu);
                     r.drop(e & 15u);
-                    continue;
+                    HASTP_LOOKUP(e, lt, kLitlenRoot, r);
+                    if ((e & kKindMask) == kLit) {
+                        *out++ = (uint16_t)((e >> 8) & 0xFFu);
+                        r.drop(e & 15u);
+                        HASTP_LOOKUP(e, lt, kLitlenRoot, r);
+                        if ((e & kKindMask) == kLit) {
+                            *out++ = (uint16_t)((e >> 8) & 0xFFu);
+                            r.drop(e & 15u);
+                            continue;
+                        }
+                    }
                 }
                 if ((e & kKindMask) == kEob) {
                     if ((e >> 16) != 0) { fail("invalid literal/length code"); ok = false; }
@@ -358,6 +368,7 @@ void decode_chunk(const uint8_t* in, size_t n, ParallelGzip::Chunk& c, const std
                 const uint32_t cl = (e >> 8) & 31u, drop = e & 63u;
                 r.drop(drop);
                 const uint32_t length = (e >> 16) + (uint32_t)((saved >> cl) & ((1u << (drop - cl)) - 1u));
+                r.refill();                                // literals may have used the budget of the distance
                 uint32_t d;
                 HASTP_LOOKUP(d, dt, kDistRoot, r);
                 if ((d & kKindMask) != kBase) { fail("invalid distance code"); ok = false; break; }
@@ -375,7 +386,14 @@ void decode_chunk(const uint8_t* in, size_t n, ParallelGzip::Chunk& c, const std
                 }
                 const uint16_t* src = out - dist;
                 uint16_t* const end = out + length;
-                if (dist >= 4) {
+                if (dist >= 8) {                           // most matches are short: 16 symbols unconditionally
+                    memcpy(out, src, 16);
+                    memcpy(out + 8, src + 8, 16);
+                    if (length > 16) {
+                        out += 16; src += 16;
+                        do { memcpy(out, src, 16); out += 8; src += 8; } while (out < end);
+                    }
+                } else if (dist >= 4) {
                     do { memcpy(out, src, 8); out += 4; src += 4; } while (out < end);
                 } else {
                     do { *out++ = *src++; } while (out < end);
@@ -399,26 +417,21 @@ void decode_chunk(const uint8_t* in, size_t n, ParallelGzip::Chunk& c, const std
     if (c.n_out > seg_begin) c.segs.push_back(Segment{seg_begin, c.n_out, false, 0, 0});
 }
 
-// 16-bit symbols -> bytes: literals are kept, placeholders read the window.  Eight at a time when none of them
-// is a placeholder (the common case away from the start of a chunk).
-void resolve_symbols(const uint16_t* sym, size_t n, const uint8_t* window, uint8_t* dst) {
+// 16-bit symbols -> bytes: literals are kept, placeholders read the window.  Sixteen at a time when none of them is
+// a placeholder; otherwise through a 64 Ki-entry table (identity below 0x8000, the window above), which has no branch
+// to mispredict -- in FASTQ the constant part of every read name is a placeholder all the way through a chunk.
+void resolve_symbols(const uint16_t* sym, size_t n, const uint8_t* lut, uint8_t* dst) {
     size_t k = 0;
     for (; k + 16 <= n; k += 16) {
         const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(sym + k));
         const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(sym + k + 8));
         if (_mm_movemask_epi8(_mm_or_si128(a, b)) & 0xAAAA) {            // some value has bit 15 set
-            for (size_t j = k; j < k + 16; ++j) {
-                const uint16_t v = sym[j];
-                dst[j] = v < kPlaceholder ? (uint8_t)v : window[v - kPlaceholder];
-            }
+            for (size_t j = k; j < k + 16; ++j) dst[j] = lut[sym[j]];
         } else {
             _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + k), _mm_packus_epi16(a, b));
         }
     }
-    for (; k < n; ++k) {
-        const uint16_t v = sym[k];
-        dst[k] = v < kPlaceholder ? (uint8_t)v : window[v - kPlaceholder];
-    }
+    for (; k < n; ++k) dst[k] = lut[sym[k]];
 }
 
 template <class F>
@@ -610,18 +623,21 @@ void ParallelGzip::run() {
             if (c.bytes.capacity() < c.n_out) { std::vector<uint8_t>().swap(c.bytes); c.bytes.reserve(c.n_out + c.n_out / 8); }
             c.bytes.resize(c.n_out);
             const uint16_t* sym = c.sym.get() + kWindow;
-            const uint8_t* w = c.window.data();
+            std::vector<uint8_t> lut(65536);
+            for (size_t v = 0; v < 256; ++v) lut[v] = (uint8_t)v;
+            memcpy(lut.data() + kPlaceholder, c.window.data(), kWindow);
+            const uint8_t* w = lut.data();
             uint8_t* dst = c.bytes.data();
-            resolve_symbols(sym, c.n_out, w, dst);
-            for (Segment& s : c.segs) {
+            // resolve and checksum block by block, while the bytes are still in cache
+            for (Segment& sg : c.segs) {
                 uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
-                size_t p = s.begin;
-                while (p < s.end) {                        // crc32() takes 32-bit lengths
-                    const size_t m = std::min<size_t>(s.end - p, (size_t)1 << 30);
+                for (size_t p = sg.begin; p < sg.end;) {
+                    const size_t m = std::min<size_t>(sg.end - p, 65536);
+                    resolve_symbols(sym + p, m, w, dst + p);
                     crc = (uint32_t)crc32(crc, dst + p, (uInt)m);
                     p += m;
                 }
-                s.crc_got = crc;
+                sg.crc_got = crc;
             }
         });
         t_ph[3] += now() - tp; tp = now();
