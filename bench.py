@@ -283,6 +283,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=1, choices=[0, 1, 2],
                     help="1 = pre-filtered fused kernel (default), 0 = direct table probe per position")
     ap.add_argument("--filter-bits", type=int, default=16, help="pre-filter bits per key")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (32/64/128), 0 = leave")
     ap.add_argument("--filter-max-mib", type=int, default=64, help="pre-filter size cap (MiB)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "hast_b200" else args.warmup
@@ -340,6 +341,8 @@ def main():
     eng.set_option("kernel", args.kernel)
     eng.set_option("filter_bits_per_key", args.filter_bits)
     eng.set_option("filter_max_bytes", args.filter_max_mib << 20)
+    if args.l2_fetch:
+        eng.set_option("l2_fetch_granularity", args.l2_fetch)
     n_keys = trio.pat.size + trio.mat.size
     eng.table_begin(spec.k, int(n_keys * args.table_scale))
     t0 = time.perf_counter()

@@ -109,6 +109,7 @@ struct hast_ctx {
     int nranks = 1, rank = 0;
 
     int tile_blocks = 0;                  // persistent grid of the tile kernels
+    int extract_blocks = 0;               // ... of tile_kernel<MODE_EXTRACT> (fewer registers: more CTAs per SM)
     int fused_blocks = 0, fused_blocks_tma = 0;   // persistent grids of classify_kernel<*, false / true>
     uint64_t filt_words = 0;
     // options (hast_set_option)
@@ -201,7 +202,7 @@ int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv, uint64_t* d_kmers,
             ctx->tv, bv, ctx->d_counts, (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull),
             ctx->d_stats, nullptr, nullptr);
     else
-        tile_kernel<MODE_EXTRACT><<<grid, kTileThreads, 0, ctx->cs>>>(ctx->tv, bv, nullptr, 0, ctx->d_stats,
+        tile_kernel<MODE_EXTRACT><<<(int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->extract_blocks), kTileThreads, 0, ctx->cs>>>(ctx->tv, bv, nullptr, 0, ctx->d_stats,
                                                                      d_kmers, d_has_n);
     CU(cudaGetLastError());
     ctx->st.kernel_launches++;
@@ -252,6 +253,8 @@ int hast_create(int device, hast_ctx** out) {
     CU_NEW(cudaMemset(ctx->d_stats, 0, sizeof(DevStats)));
     int per_sm = 0;
     CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel<MODE_CLASSIFY>, kTileThreads, 0));
+    int per_sm_x = 0;
+    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_x, tile_kernel<MODE_EXTRACT>, kTileThreads, 0));
     // classify_kernel keeps its pass in dynamic shared memory (opt-in above 48 KiB for the TMA variant)
 #define HAST_ATTR(KT)                                                                                              \
     CU_NEW(cudaFuncSetAttribute(classify_kernel<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
@@ -272,6 +275,7 @@ int hast_create(int device, hast_ctx** out) {
     ctx->fused_blocks_tma = std::max(1, per_sm_t) * prop.multiProcessorCount;
 #undef CU_NEW
     ctx->tile_blocks = std::max(1, per_sm) * ctx->sm_count;
+    ctx->extract_blocks = std::max(1, per_sm_x) * ctx->sm_count;
     ctx->fused_blocks = std::max(1, per_sm_f) * ctx->sm_count;
     *out = ctx;
     return HAST_OK;
@@ -320,6 +324,12 @@ int hast_set_option(hast_ctx* ctx, const char* name, int64_t value) {
     } else if (n == "filter_max_bytes") {
         if (value < 128) return fail(ctx, HAST_E_ARG, "filter_max_bytes: >= 128");
         ctx->opt_filter_max_bytes = value;
+    } else if (n == "l2_fetch_granularity") {
+        // device-wide hint (cudaLimitMaxL2FetchGranularity): bytes fetched from HBM on an L2 miss.  The table
+        // probes and count-table updates touch one 32-byte sector per access.
+        if (value != 32 && value != 64 && value != 128) return fail(ctx, HAST_E_ARG, "l2_fetch_granularity: 32, 64 or 128");
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
     } else {
         return fail(ctx, HAST_E_ARG, "unknown option: " + n);
     }

@@ -109,7 +109,7 @@ tile_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_b
             uint8_t* __restrict__ has_n_out) {
     __shared__ uint32_t s_off[kReadsPerTile + 1];
     __shared__ uint32_t s_votes[kReadsPerTile];
-    __shared__ uint32_t s_packed[kTileWords + 2];
+    __shared__ uint32_t s_packed[kTileWords + 4];
     __shared__ uint32_t s_bad[kTileWords / 2 + 1];
 
     const uint32_t tid = threadIdx.x;
@@ -152,7 +152,7 @@ tile_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_b
             __syncthreads();
 
             // (a) pack
-            for (uint32_t seg = tid; seg < nseg + 2; seg += kTileThreads) {
+            for (uint32_t seg = tid; seg < nseg + 4; seg += kTileThreads) {
                 uint32_t word = 0;
                 if (seg < nseg) {
                     const uint64_t g = (uint64_t)lo + 16ull * seg;
@@ -207,6 +207,43 @@ tile_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_b
 
             // (c) per k-mer position
             const uint32_t pbeg = s_off[ra] - lo, pend = hi - lo;
+            if (MODE == MODE_EXTRACT) {
+                // K2 alone is a streaming kernel (8 bytes out per position): four consecutive positions per thread,
+                // the first cut out of the packed stream, the other three ROLLED from it (kmer.h:109-127 does the
+                // same on its 128-bit words), written as two 16-byte stores, so a warp writes 1 KiB in one piece.
+                // Positions that start no k-mer get all ones.
+                const int km = k;
+                const uint32_t rc_shift = 2u * (uint32_t)(km - 1);
+                for (uint32_t q = (pbeg & ~3u) + 4u * tid; q < pend; q += 4u * kTileThreads) {
+                    const uint64_t x = window64(s_packed, q);
+                    uint64_t fwd = x >> (64 - 2 * km);
+                    uint64_t rcv = revcomp_top(x, kmask);
+                    // the three bases that enter next: positions q+k .. q+k+2
+                    const uint32_t nb = q + (uint32_t)km;
+                    const uint32_t wn = __funnelshift_l(s_packed[(nb >> 4) + 1], s_packed[nb >> 4], (nb & 15u) * 2u);
+                    const uint32_t bad4 = (s_bad[q >> 5] >> (q & 31u)) & 15u;     // q is a multiple of 4: one word
+                    uint64_t v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j) {
+                            const uint64_t c = (wn >> (32 - 2 * j)) & 3u;
+                            fwd = ((fwd << 2) | c) & kmask;
+                            rcv = (rcv >> 2) | ((c ^ 2ull) << rc_shift);
+                        }
+                        const uint64_t canon = fwd < rcv ? fwd : rcv;
+                        v[j] = ((bad4 >> j) & 1u) ? ~0ull : canon;
+                    }
+                    uint64_t* dst = kmers_out + (uint64_t)lo + q;
+                    if (q >= pbeg && q + 4 <= pend && (((uintptr_t)dst) & 15u) == 0) {
+                        asm volatile("st.global.v2.u64 [%0], {%1,%2};" :: "l"(dst), "l"(v[0]), "l"(v[1]) : "memory");
+                        asm volatile("st.global.v2.u64 [%0], {%1,%2};" :: "l"(dst + 2), "l"(v[2]), "l"(v[3]) : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (q + j >= pbeg && q + j < pend) dst[j] = v[j];
+                    }
+                }
+            } else
             for (uint32_t base = pbeg; base < pend; base += kTileThreads * kProbeUnroll) {
                 uint64_t canon[kProbeUnroll];
                 uint64_t want[kProbeUnroll];

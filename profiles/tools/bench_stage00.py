@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--coverage", type=float, default=30.0)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--l2-fetch", type=int, default=0)
     args = ap.parse_args()
     import torch
     from hast_b200 import synth
@@ -47,6 +48,8 @@ def main():
     SUB = 2_000_000
     d_off = (torch.arange(SUB + 1, dtype=torch.int64, device=dev) * L).to(torch.int32)
     eng = Engine(0)
+    if args.l2_fetch:
+        eng.set_option("l2_fetch_granularity", args.l2_fetch)
     expected = int(2.2 * args.genome * (1 + args.coverage * 0.003 * k))       # genomic + error k-mers, both parents
     out = {}
 
