@@ -280,8 +280,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--table-scale", type=float, default=1.0, help="expected_keys multiplier (sparser table)")
-    ap.add_argument("--kernel", type=int, default=1, choices=[0, 1, 2],
-                    help="1 = pre-filtered fused kernel (default), 0 = direct table probe per position")
+    ap.add_argument("--kernel", type=int, default=1, choices=[0, 1, 2, 3],
+                    help="3 = pre-filtered fused kernel, filter word chosen by the k-mer's minimizer (default), "
+                         "1 = filter word chosen by a hash of the k-mer, 2 = as 1 with TMA-staged reads, "
+                         "0 = direct table probe per position")
     ap.add_argument("--filter-bits", type=int, default=16, help="pre-filter bits per key")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (32/64/128), 0 = leave")
     ap.add_argument("--filter-max-mib", type=int, default=64, help="pre-filter size cap (MiB)")
@@ -538,6 +540,7 @@ def main():
                 "stats": {"reads_with_n": st["reads_with_n"] // args.steps, "extra_probes": st["extra_probes"] // args.steps,
                           "filter_pass_per_step": st["filter_pass"] // args.steps,
                           "filter_pass_frac": st["filter_pass"] / max(1, st["lookups"]),
+                          "filter_loads_per_lookup": st["filter_loads"] / max(1, st["lookups"]),
                           "filter_bytes": int(info.filter_bytes), "kernel": args.kernel}}
         emit(line)
     eng.close()

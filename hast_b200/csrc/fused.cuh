@@ -101,6 +101,17 @@ __device__ __forceinline__ uint64_t load_filter(const uint64_t* p, uint64_t pol)
     return v;
 }
 
+// the same under a predicate that the compiler cannot see through: with a plain `if (p) v = load`, ptxas
+// folds the sweep's "keep the previous word" select into the load's destination register, which makes
+// every fetch wait for the one before it (measured: the sweep then runs at one L2 latency per fetch)
+__device__ __forceinline__ uint64_t load_filter_if(const uint64_t* p, uint64_t pol, uint32_t on) {
+    uint64_t v = 0ull;
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\n"
+                 "@q ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;\n}"
+                 : "+l"(v) : "l"(p), "l"(pol), "r"(on));
+    return v;
+}
+
 // 16 read bytes, used once: do not let them push the filter / table out of L2
 __device__ __forceinline__ uint4 load_stream16_ef(const uint8_t* p, uint64_t pol) {
     uint4 v;
@@ -147,7 +158,12 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 // (the lists are jellyfish dumps: upper-case ACGT); a window over anything else ('N', lower case, '\r')
 // simply does not match -- it does not silence the rest of the sequence -- and a sequence shorter than
 // k is not an error.  "Reads" are chunks of a sequence, "barcodes" are sequence ids.
-template <int KT, bool TMA, bool PACKED = false, bool SEQ = false>
+// MINI (KT > 0 with mini_len(KT) > 0 only): the filter word of a position is chosen by the k-mer's
+// minimizer (table.cuh), so a thread walking its 16 neighbouring positions fetches a new filter word
+// only where the minimizer changes (~2/(k-m+2) of the positions) instead of at every position.  The
+// sweep was bound by the one-divergent-request-per-clock limit of the L1 (profiles/r01_c); this trades
+// ~15 integer instructions per position for ~70 % of those requests.
+template <int KT, bool TMA, bool PACKED = false, bool SEQ = false, bool MINI = false>
 __global__ void __launch_bounds__(kTileThreads, 4)
 classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_barcodes,
                 DevStats* __restrict__ stats) {
@@ -178,7 +194,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
     const uint32_t nxt_word = (uint32_t)km1 >> 4, nxt_sh = ((uint32_t)km1 & 15u) * 2u;
 
     unsigned long long st_lookups = 0, st_n = 0, st_short = 0, st_long = 0, st_badbc = 0;
-    uint32_t st_extra = 0, st_pass = 0;
+    uint32_t st_extra = 0, st_pass = 0, st_loads = 0;
 
     // The read bytes of pass i+1 are streamed into sm.raw by one bulk copy while pass i is being
     // swept (raw is only needed until pass i has been packed).  Thread 0 issues, everybody waits
@@ -240,45 +256,64 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
             }
             __syncthreads();
 
-            // (a) pack: 16 ASCII bytes -> one 2-bit word; 'N' bytes flagged
-            for (uint32_t seg = tid; seg < nseg + 4; seg += kTileThreads) {
-                uint32_t word = 0;
-                if (PACKED) {
-                    if (seg < nseg) {
+            // (a) pack: 16 ASCII bytes -> one 2-bit word; 'N' bytes flagged.  kPackUnroll segments per thread
+            // are fetched before the first is packed, so a pass pays the DRAM latency of its ~10 segments
+            // per thread three times instead of ten
+            constexpr int kPackUnroll = 4;
+            for (uint32_t seg0 = tid; seg0 < nseg + 4; seg0 += kTileThreads * kPackUnroll) {
+                uint4 v[kPackUnroll];
+                bool full[kPackUnroll];
+#pragma unroll
+                for (int u = 0; u < kPackUnroll; ++u) {
+                    const uint32_t seg = seg0 + (uint32_t)u * kTileThreads;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    full[u] = false;
+                    if (seg >= nseg) continue;
+                    if (PACKED) {
                         const uint32_t gw = (lo >> 4) + seg;
                         if ((uint64_t)gw * 16u < b.n_bases)
                             asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;"
-                                         : "=r"(word) : "l"(b.packed + gw), "l"(pol_first));
-                    }
-                } else if (seg < nseg) {
-                    uint4 v;
-                    if (TMA) {
-                        v = *reinterpret_cast<const uint4*>(sm.raw + 16u * seg);
+                                         : "=r"(v[u].x) : "l"(b.packed + gw), "l"(pol_first));
+                    } else if (TMA) {
+                        v[u] = *reinterpret_cast<const uint4*>(sm.raw + 16u * seg);
+                        full[u] = true;
                     } else {
                         const uint64_t g = (uint64_t)lo + 16ull * seg;
-                        if (g + 16 <= b.n_bases) {
-                            v = load_stream16_ef(b.bases + g, pol_first);
-                        } else {                           // last, partial segment of the batch
+                        full[u] = g + 16 <= b.n_bases;
+                        if (full[u]) v[u] = load_stream16_ef(b.bases + g, pol_first);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kPackUnroll; ++u) {
+                    const uint32_t seg = seg0 + (uint32_t)u * kTileThreads;
+                    if (seg >= nseg + 4) continue;
+                    uint32_t word = 0;
+                    if (PACKED) {
+                        word = v[u].x;
+                    } else if (seg < nseg) {
+                        uint4 x = v[u];
+                        if (!full[u]) {                        // last, partial segment of the batch
+                            const uint64_t g = (uint64_t)lo + 16ull * seg;
                             uint32_t w[4] = {0, 0, 0, 0};
                             for (uint32_t j = 0; j < 16 && g + j < b.n_bases; ++j)
                                 w[j >> 2] |= (uint32_t)b.bases[g + j] << (8 * (j & 3));
-                            v = make_uint4(w[0], w[1], w[2], w[3]);
+                            x = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                        word = pack16(x);
+                        if (SEQ) {
+                            const uint32_t m16 = not_acgt4(x.x) | (not_acgt4(x.y) << 4) | (not_acgt4(x.z) << 8) |
+                                                 (not_acgt4(x.w) << 12);
+                            if (m16) atomicOr(&s_bad[seg >> 1], m16 << ((seg & 1u) * 16u));
+                        } else if (any_N4(x.x) | any_N4(x.y) | any_N4(x.z) | any_N4(x.w)) {
+                            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+                            uint32_t m16 = 0;
+                            for (uint32_t j = 0; j < 16; ++j)
+                                if (((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) == 'N') m16 |= 1u << j;
+                            atomicOr(&s_bad[seg >> 1], m16 << ((seg & 1u) * 16u));
                         }
                     }
-                    word = pack16(v);
-                    if (SEQ) {
-                        const uint32_t m16 = not_acgt4(v.x) | (not_acgt4(v.y) << 4) | (not_acgt4(v.z) << 8) |
-                                             (not_acgt4(v.w) << 12);
-                        if (m16) atomicOr(&s_bad[seg >> 1], m16 << ((seg & 1u) * 16u));
-                    } else if (any_N4(v.x) | any_N4(v.y) | any_N4(v.z) | any_N4(v.w)) {
-                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                        uint32_t m16 = 0;
-                        for (uint32_t j = 0; j < 16; ++j)
-                            if (((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) == 'N') m16 |= 1u << j;
-                        atomicOr(&s_bad[seg >> 1], m16 << ((seg & 1u) * 16u));
-                    }
+                    s_packed[seg] = word;
                 }
-                s_packed[seg] = word;
             }
             __syncthreads();
             // sm.raw is free again: stream in the next pass (of this tile, else of the next tile)
@@ -348,6 +383,72 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                     const uint64_t x = ((uint64_t)w0 << 32) | w1;
                     uint64_t fwd = km1 ? (x >> fwd_init_shift) : 0ull;
                     uint64_t rcv = revcomp_top(x, mask_km1) << 2;
+                    // MINI: filter word index of each of the 16 positions, and the positions that must fetch
+                    constexpr int kM = MINI ? mini_len(KT) : 1, kW = MINI ? KT - kM + 1 : 1, kT = 16 + kW - 1;
+                    uint32_t idx[MINI ? 16 : 1];
+                    uint32_t need = valid;
+                    uint64_t cur = 0ull;
+                    if (MINI) {
+                        // hashes of the canonical m-mers at bases 0 .. kT-1 of this thread's 48-base window;
+                        // the reverse strand comes from the window's reverse complement (base i <-> 47-i)
+                        const uint32_t w2 = s_packed[wi + 2];
+                        const uint32_t r0 = revcomp16(w2), r1 = revcomp16(w1), r2 = revcomp16(w0);
+                        uint32_t hm[kT];
+#pragma unroll
+                        for (int tt = 0; tt < kT; ++tt) {
+                            const uint32_t fwin = tt == 0 ? w0 : tt < 16 ? __funnelshift_l(w1, w0, 2 * tt)
+                                                : tt == 16 ? w1 : __funnelshift_l(w2, w1, 2 * (tt - 16));
+                            const int q = 48 - tt - kM;            // first base of the mirrored m-mer
+                            const uint32_t rwin = q >= 32 ? (r2 << (2 * (q - 32)))
+                                                : q >= 16 ? __funnelshift_l(r2, r1, 2 * (q - 16))
+                                                          : __funnelshift_l(r1, r0, 2 * q);
+                            const uint32_t f = fwin >> (32 - 2 * kM), r = rwin >> (32 - 2 * kM);
+                            hm[tt] = mini_hash(f < r ? f : r);
+                        }
+                        // sliding minimum over kW hashes by doubling: after step s, hm[i] = min hm[i .. i+2s-1]
+                        int span = 1;
+#pragma unroll
+                        for (int s = 1; 2 * s <= kW; s *= 2) {
+#pragma unroll
+                            for (int i = 0; i + s < kT; ++i) hm[i] = min(hm[i], hm[i + s]);
+                            span = 2 * s;
+                        }
+                        uint32_t chg = 1u;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t mn = span == kW ? hm[j] : min(hm[j], hm[j + kW - span]);
+                            idx[j] = mini_word(mn) >> t.filt_shift;
+                            if (j) chg |= (uint32_t)(idx[j] != idx[j - 1]) << j;
+                        }
+                        need = valid & (chg | ~(valid << 1));      // word changed, or the position before holds none
+                    }
+                    st_loads += __popc(need);
+                    if (MINI) {
+                        // all fetches first, then the k-mer work of the 16 positions while they are in flight
+                        uint64_t fw[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            fw[j] = load_filter_if(t.filt + idx[MINI ? j : 0], pol_last, (need >> j) & 1u);
+                        }
+                        uint32_t hbp[8];                           // bit selectors, two positions per register
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t c = (nxt >> (30 - 2 * j)) & 3u;
+                            fwd = ((fwd << 2) | c) & kmask;
+                            rcv = (rcv >> 2) | ((uint64_t)(c ^ 2u) << rc_shift);
+                            const uint64_t canon = fwd < rcv ? fwd : rcv;
+                            const uint32_t sel = filter_hash(canon).bits >> 22;     // 5 + 5 bits
+                            hbp[j >> 1] = (j & 1) ? (hbp[j >> 1] | (sel << 16)) : sel;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if ((need >> j) & 1u) cur = fw[j];     // positions in between keep the last fetched word
+                            const uint32_t sel = hbp[j >> 1] >> ((j & 1) * 16);
+                            const uint32_t hit = ((uint32_t)cur >> ((sel >> 5) & 31u)) & ((uint32_t)(cur >> 32) >> (sel & 31u)) &
+                                                 (valid >> j) & 1u;
+                            pass |= hit << j;
+                        }
+                    } else {
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         uint64_t fw[8];
@@ -370,6 +471,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                                                  ((uint32_t)(fw[u] >> 32) >> ((hb[u] >> 22) & 31u)) & 1u;
                             pass |= hit << (half * 8 + u);
                         }
+                    }
                     }
                 }
                 // append the passing positions to the queue: one shared atomic per warp; no
@@ -489,6 +591,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
         st_badbc += __shfl_xor_sync(0xFFFFFFFFu, st_badbc, o);
         st_extra += __shfl_xor_sync(0xFFFFFFFFu, st_extra, o);
         st_pass += __shfl_xor_sync(0xFFFFFFFFu, st_pass, o);
+        st_loads += __shfl_xor_sync(0xFFFFFFFFu, st_loads, o);
     }
     if (lane == 0) {
         if (st_lookups) atomicAdd(&stats->lookups, st_lookups);
@@ -498,6 +601,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
         if (st_badbc) atomicAdd(&stats->bad_barcode, st_badbc);
         if (st_extra) atomicAdd(&stats->extra_probes, (unsigned long long)st_extra);
         if (st_pass) atomicAdd(&stats->filter_pass, (unsigned long long)st_pass);
+        if (st_loads) atomicAdd(&stats->filter_loads, (unsigned long long)st_loads);
     }
 }
 

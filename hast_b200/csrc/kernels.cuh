@@ -30,6 +30,7 @@ struct DevStats {
     unsigned long long reads_too_long;
     unsigned long long bad_barcode;
     unsigned long long filter_pass;
+    unsigned long long filter_loads;
 };
 
 struct BatchView {
@@ -370,7 +371,12 @@ __device__ __forceinline__ void table_insert(const TableView& t, uint64_t canon,
     const uint64_t tagbits = (uint64_t)(1u << parent) << 1;
     {   // pre-filter first: a key must never be in the table without its filter bits
         const FilterHash fh = filter_hash(canon);
-        unsigned long long* fw = (unsigned long long*)(t.filt + (fh.word >> t.filt_shift));
+        uint32_t word = fh.word;
+        if (t.filt_m) {                                    // minimizer-addressed filter (table.cuh)
+            const uint64_t rc = revcomp_top(t.k < 32 ? (canon << (64 - 2 * t.k)) : canon, t.kmask);
+            word = mini_word(minimizer_hash(canon, rc, t.k, (int)t.filt_m));
+        }
+        unsigned long long* fw = (unsigned long long*)(t.filt + (word >> t.filt_shift));
         const unsigned long long bits = filter_bits(fh);
         if ((*(volatile unsigned long long*)fw & bits) != bits) atomicOr(fw, bits);
     }

@@ -37,6 +37,12 @@ __device__ __forceinline__ uint64_t revcomp_top(uint64_t x, uint64_t mask) {
     return y & mask;
 }
 
+// reverse complement of all 16 bases of one packed word
+__device__ __forceinline__ uint32_t revcomp16(uint32_t w) {
+    const uint32_t y = __brev(w ^ 0xAAAAAAAAu);
+    return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+}
+
 // 16 ASCII bases (one 128-bit load) -> one 32-bit word, first base in the top
 // two bits.  Per 4 bytes: codes = (w >> 1) & 0x03030303 leaves base i in byte i;
 // the multiply gathers the four 2-bit fields into the top byte with no carries

@@ -43,6 +43,9 @@ struct TableView {
     // 64-bit words, two bits per key, one in each half of the key's word
     uint64_t* filt;
     uint32_t filt_shift;
+    // 0: the filter word is picked by a hash of the k-mer itself; m > 0: by the k-mer's MINIMIZER of
+    // length m (below), so that neighbouring positions of a read mostly share one filter word
+    uint32_t filt_m;
 };
 
 // multiply / xor-shift / multiply, every step a bijection of Z/2^(2k)
@@ -74,6 +77,36 @@ __host__ __device__ __forceinline__ uint32_t filter_bit_lo(FilterHash f) { retur
 __host__ __device__ __forceinline__ uint32_t filter_bit_hi(FilterHash f) { return (f.bits >> 22) & 31u; }
 __host__ __device__ __forceinline__ uint64_t filter_bits(FilterHash f) {
     return (1ull << filter_bit_lo(f)) | (1ull << (32u + filter_bit_hi(f)));
+}
+
+// ---- minimizer-addressed pre-filter ------------------------------------------------------
+// The k-mer's filter WORD is chosen by its minimizer: over the k-m+1 m-mers s inside the k-mer,
+// the smallest value of  mini_hash(min(s, revcomp(s))).  The set of canonical m-mers is the same
+// for a k-mer and its reverse complement, so the choice is orientation-free, and consecutive
+// k-mers of a sequence share their minimizer for (k-m+2)/2 positions on average: a thread that
+// walks 16 neighbouring positions needs ~0.3 filter loads per position instead of one (fused.cuh,
+// the MINI sweep).  The two bits inside the word still come from the k-mer's own hash
+// (filter_hash().bits), so the filter stays a per-k-mer membership test.
+// Minimizer lengths: long enough that a human genome's minimizers far outnumber the filter words.
+constexpr uint32_t kMiniC = 0x9E3779B1u, kMiniD = 0x7F4A7C15u, kMiniC2 = 0x85EBCA77u;
+__host__ __device__ __forceinline__ constexpr int mini_len(int k) {
+    return (k == 21 || k == 25 || k == 31) ? 15 : k == 17 ? 13 : 0;      // 0: no minimizer sweep for this k
+}
+__host__ __device__ __forceinline__ uint32_t mini_hash(uint32_t canon_mmer) { return canon_mmer * kMiniC + kMiniD; }
+// top bits pick the filter word (the minimum of several hashes is biased towards 0: remix it)
+__host__ __device__ __forceinline__ uint32_t mini_word(uint32_t min_hash) { return min_hash * kMiniC2; }
+// minimizer hash of one k-mer given both strands right-aligned (fwd, rc = its reverse complement)
+__host__ __device__ __forceinline__ uint32_t minimizer_hash(uint64_t fwd, uint64_t rc, int k, int m) {
+    const uint32_t mmask = (uint32_t)((1ull << (2 * m)) - 1ull);
+    uint32_t best = 0xFFFFFFFFu;
+    for (int i = 0; i + m <= k; ++i) {
+        // the m-mer at offset i from the right end of fwd; its reverse complement sits at the mirrored offset of rc
+        const uint32_t a = (uint32_t)(fwd >> (2 * i)) & mmask;
+        const uint32_t b = (uint32_t)(rc >> (2 * (k - m - i))) & mmask;
+        const uint32_t h = mini_hash(a < b ? a : b);
+        best = h < best ? h : best;
+    }
+    return best;
 }
 
 #ifdef __CUDACC__

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HAST_ABI_VERSION 3
+#define HAST_ABI_VERSION 4
 
 #define HAST_OK            0
 #define HAST_E_ARG        -1   /* bad argument                                            */
@@ -64,6 +64,7 @@ typedef struct hast_stats {
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
     uint64_t filter_pass;      /* lookups the pre-filter sent on to the exact table       */
+    uint64_t filter_loads;     /* 8-byte pre-filter words fetched (minimizer sweep: < lookups) */
 } hast_stats;
 
 /* ---- library / context ------------------------------------------------- */
@@ -74,8 +75,11 @@ int          hast_create(int device, hast_ctx **out);
 void         hast_destroy(hast_ctx *ctx);
 const char  *hast_last_error(const hast_ctx *ctx);      /* ctx may be NULL */
 int          hast_device(const hast_ctx *ctx);
-/* Tuning knobs, set before hast_table_begin: "kernel" (1 = pre-filtered fused
- * kernel, default; 0 = direct table probe per position), "filter_bits_per_key"
+/* Tuning knobs, set before hast_table_begin: "kernel" (3 = pre-filtered fused
+ * kernel whose filter word is chosen by the k-mer's minimizer, default for
+ * k = 17/21/25/31; 1 = filter word chosen by a hash of the k-mer, what every
+ * other k runs; 2 = as 1 with TMA-staged reads; 0 = direct table probe per
+ * position; 1/2 <-> 3 takes effect at the next hast_table_begin), "filter_bits_per_key"
  * (default 16), "filter_max_bytes" (default 64 MiB: the filter is meant to stay
  * L2-resident).  None of them changes any result.  "seq_mode" = 1 switches the
  * fused kernel to the window rule of HAST stage 03 (03.mkoutput_by_fabulous2.0/

@@ -20,8 +20,25 @@ def revcomp_ascii(s: bytes) -> bytes:
     return bytes(COMP[c] for c in reversed(s))
 
 
+def low_complexity_genome(rng, n: int = 4000) -> bytes:
+    """Homopolymer runs and short tandem repeats with a few random stretches in between: every k-mer
+    shares its few distinct m-mers (hence its minimizer) with many others, and most windows are their
+    neighbours' reverse complement or a rotation of them."""
+    out = bytearray()
+    while len(out) < n:
+        u = rng.random()
+        if u < 0.25:
+            out += bytes([int(LET[rng.integers(0, 4)])]) * int(rng.integers(20, 120))
+        elif u < 0.8:
+            unit = LET[rng.integers(0, 4, int(rng.integers(2, 7)))].tobytes()
+            out += unit * int(rng.integers(8, 40))
+        else:
+            out += LET[rng.integers(0, 4, int(rng.integers(5, 60)))].tobytes()
+    return bytes(out[:n])
+
+
 def adversarial_case(k: int, n_reads: int, seed: int, min_len: int | None = None, max_len: int = 160,
-                     n_barcodes: int = 37, with_adaptor: bool = True):
+                     n_barcodes: int = 37, with_adaptor: bool = True, low_complexity: bool = False):
     """Returns dict(pat_text, mat_text, reads=[bytes], heads=[bytes], bc_ids, bc_names).
 
     The k-mer lists are drawn from the reads themselves (so hits are common),
@@ -30,7 +47,7 @@ def adversarial_case(k: int, n_reads: int, seed: int, min_len: int | None = None
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     min_len = k if min_len is None else min_len
-    genome = LET[rng.integers(0, 4, 4000)].tobytes()
+    genome = low_complexity_genome(rng) if low_complexity else LET[rng.integers(0, 4, 4000)].tobytes()
     reads = []
     for i in range(n_reads):
         L = int(rng.integers(min_len, max_len + 1))

@@ -216,6 +216,45 @@ def test_table_under_pressure(engine):
     assert st["extra_probes"] > 0
 
 
+@pytest.mark.parametrize("k", [17, 21, 25, 31, 32])
+def test_low_complexity_parity(engine, k):
+    """Homopolymers and short tandem repeats: thousands of distinct k-mers share one minimizer, so the
+    minimizer-addressed pre-filter saturates a few words and leaves the decision to the exact table."""
+    case = cases.adversarial_case(k, 3000, seed=900 + k, low_complexity=True)
+    build_table(engine, case)
+    o, _ = build_oracle(case)
+    bases, off = cases.flatten(case["reads"])
+    want, lookups = o.classify_batch(bases, off, case["bc_ids"], len(case["bc_names"]))
+    got, st = run_fused(engine, case, split=[777])
+    assert (got == want).all() and want.sum() > 0
+    assert st["lookups"] == lookups
+
+
+def test_minimizer_sweep_fetches_fewer_filter_words(request):
+    """kernel 3 and kernel 1 give identical counts on the cfg1-scale trio; the minimizer sweep fetches a new
+    pre-filter word only where the minimizer changes (about 2/(k-m+2) of the positions plus read starts),
+    the per-k-mer sweep one word per position."""
+    from hast_b200.capi import Engine
+    t = synth.make_trio(synth.config("small"))
+    bases, off, bc = t.batch()
+    res = {}
+    for kern in (3, 1):
+        with Engine(0) as e:
+            e.set_option("kernel", kern)
+            e.table_begin(t.spec.k, t.pat.size + t.mat.size)
+            e.table_add_packed(t.pat, 0)
+            e.table_add_packed(t.mat, 1)
+            e.reserve_barcodes(t.n_barcodes)
+            e.submit_batch(bases, off, bc)
+            res[kern] = (e.finish(t.n_barcodes), e.stats())
+    assert (res[3][0] == res[1][0]).all() and res[3][0].sum() > 0
+    s3, s1 = res[3][1], res[1][1]
+    assert s1["lookups"] == s3["lookups"] and s1["filter_loads"] == s1["lookups"]
+    assert 0 < s3["filter_loads"] < 0.45 * s3["lookups"]
+    # the filter stays selective: members plus a few per cent of false positives
+    assert s3["filter_pass"] < 0.15 * s3["lookups"]
+
+
 def test_saturated_filter_queue_drains(engine):
     """A pre-filter far too small for the key set passes (almost) every position, so the
     shared-memory queue fills and drains every sweep; the exact table still decides."""
