@@ -385,61 +385,60 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                     uint64_t rcv = revcomp_top(x, mask_km1) << 2;
                     // MINI: filter word index of each of the 16 positions, and the positions that must fetch
                     constexpr int kM = MINI ? mini_len(KT) : 1, kW = MINI ? KT - kM + 1 : 1, kT = 16 + kW - 1;
+                    static_assert(!MINI || (kM == 16 && kT <= 32), "the MINI sweep works on 16-base windows of a 48-base stretch");
                     uint32_t idx[MINI ? 16 : 1];
                     uint32_t need = valid;
                     uint64_t cur = 0ull;
                     if (MINI) {
-                        // hashes of the canonical m-mers at bases 0 .. kT-1 of this thread's 48-base window;
-                        // the reverse strand comes from the window's reverse complement (base i <-> 47-i)
+                        // Everything comes from the 32-bit windows f[t] = bases t .. t+15 of this thread's 48-base
+                        // stretch and g[t] = their reverse complements (cut out of the stretch's reverse complement,
+                        // base i <-> 47-i), t = 0 .. kT-1:
+                        //   m-mer (m = 16) at t, canonical:  min(f[t], g[t])           -> mini_hash -> sliding minimum
+                        //   k-mer at j: first / last 16 bases f[j], f[j+kW-1]; of its reverse complement g[j+kW-1], g[j]
+                        //               -> mini_sel, a symmetric function of the two strands (no canonical compare)
                         const uint32_t w2 = s_packed[wi + 2];
                         const uint32_t r0 = revcomp16(w2), r1 = revcomp16(w1), r2 = revcomp16(w0);
-                        uint32_t hm[kT];
+                        uint32_t hm[kT], sa[16], selv[16];
 #pragma unroll
                         for (int tt = 0; tt < kT; ++tt) {
-                            const uint32_t fwin = tt == 0 ? w0 : tt < 16 ? __funnelshift_l(w1, w0, 2 * tt)
-                                                : tt == 16 ? w1 : __funnelshift_l(w2, w1, 2 * (tt - 16));
-                            const int q = 48 - tt - kM;            // first base of the mirrored m-mer
-                            const uint32_t rwin = q >= 32 ? (r2 << (2 * (q - 32)))
-                                                : q >= 16 ? __funnelshift_l(r2, r1, 2 * (q - 16))
-                                                          : __funnelshift_l(r1, r0, 2 * q);
-                            const uint32_t f = fwin >> (32 - 2 * kM), r = rwin >> (32 - 2 * kM);
-                            hm[tt] = mini_hash(f < r ? f : r);
+                            const uint32_t f = tt == 0 ? w0 : tt < 16 ? __funnelshift_l(w1, w0, 2 * tt)
+                                             : tt == 16 ? w1 : __funnelshift_l(w2, w1, 2 * (tt - 16));
+                            const int q = 32 - tt;                 // first base of the mirrored window
+                            const uint32_t g = q >= 32 ? r2 : q >= 16 ? __funnelshift_l(r2, r1, 2 * (q - 16))
+                                                                      : __funnelshift_l(r1, r0, 2 * q);
+                            hm[tt] = mini_hash(min(f, g));
+                            if (tt < 16) sa[tt] = f * kSelC1 + g * kSelC2;
+                            if (tt >= kW - 1) selv[tt - (kW - 1)] = (sa[tt - (kW - 1)] + f * kSelC2 + g * kSelC1) >> 22;
                         }
-                        // sliding minimum over kW hashes by doubling: after step s, hm[i] = min hm[i .. i+2s-1]
-                        int span = 1;
+                        // sliding minimum over kW hashes: windows of 3, then of 9, then two or three of those
+                        constexpr int kWd1 = kW >= 3 ? 3 : 1, kWd = kW >= 9 ? 9 : kWd1;
+                        if (kW >= 3) {
 #pragma unroll
-                        for (int s = 1; 2 * s <= kW; s *= 2) {
+                            for (int i = 0; i + 2 < kT; ++i) hm[i] = min(min(hm[i], hm[i + 1]), hm[i + 2]);
+                        }
+                        if (kW >= 9) {
 #pragma unroll
-                            for (int i = 0; i + s < kT; ++i) hm[i] = min(hm[i], hm[i + s]);
-                            span = 2 * s;
+                            for (int i = 0; i + 8 < kT; ++i) hm[i] = min(min(hm[i], hm[i + 3]), hm[i + 6]);
                         }
                         uint32_t chg = 1u;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const uint32_t mn = span == kW ? hm[j] : min(hm[j], hm[j + kW - span]);
+                            const uint32_t mn = kWd == kW ? hm[j]
+                                              : 2 * kWd >= kW ? min(hm[j], hm[j + kW - kWd])
+                                                              : min(min(hm[j], hm[j + kWd]), hm[j + kW - kWd]);
                             idx[j] = mini_word(mn) >> t.filt_shift;
                             if (j) chg |= (uint32_t)(idx[j] != idx[j - 1]) << j;
                         }
                         need = valid & (chg | ~(valid << 1));      // word changed, or the position before holds none
-                    }
-                    st_loads += __popc(need);
-                    if (MINI) {
-                        // all fetches first, then the k-mer work of the 16 positions while they are in flight
+                        st_loads += __popc(need);
+                        // all fetches first; the selectors are packed two per register while they are in flight
                         uint64_t fw[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            fw[j] = load_filter_if(t.filt + idx[MINI ? j : 0], pol_last, (need >> j) & 1u);
-                        }
-                        uint32_t hbp[8];                           // bit selectors, two positions per register
+                        for (int j = 0; j < 16; ++j)
+                            fw[j] = load_filter_if(t.filt + idx[j], pol_last, (need >> j) & 1u);
+                        uint32_t hbp[8];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const uint32_t c = (nxt >> (30 - 2 * j)) & 3u;
-                            fwd = ((fwd << 2) | c) & kmask;
-                            rcv = (rcv >> 2) | ((uint64_t)(c ^ 2u) << rc_shift);
-                            const uint64_t canon = fwd < rcv ? fwd : rcv;
-                            const uint32_t sel = filter_hash(canon).bits >> 22;     // 5 + 5 bits
-                            hbp[j >> 1] = (j & 1) ? (hbp[j >> 1] | (sel << 16)) : sel;
-                        }
+                        for (int j = 0; j < 8; ++j) hbp[j] = selv[2 * j] | (selv[2 * j + 1] << 16);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             if ((need >> j) & 1u) cur = fw[j];     // positions in between keep the last fetched word
@@ -449,6 +448,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                             pass |= hit << j;
                         }
                     } else {
+                    st_loads += __popc(valid);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         uint64_t fw[8];

@@ -113,7 +113,7 @@ struct hast_ctx {
     int fused_blocks = 0, fused_blocks_tma = 0;   // persistent grids of classify_kernel<*, false / true>
     uint64_t filt_words = 0;
     // options (hast_set_option)
-    int64_t opt_kernel = 1;               // 3 = classify_kernel with the minimizer-addressed pre-filter (k = 17/21/25/31; other k run as 1),
+    int64_t opt_kernel = 3;               // 3 = classify_kernel with the minimizer-addressed pre-filter (k = 17/21/25/31; other k run as 1),
                                           // 1 = classify_kernel (per-k-mer filter word), 2 = same with TMA-staged reads, 0 = tile_kernel<MODE_CLASSIFY>
     int64_t opt_seq_mode = 0;             // 1 = stage-03 window rule (classify_kernel<.., SEQ>)
     int64_t opt_filter_bits_per_key = 16;
@@ -277,7 +277,7 @@ int hast_create(int device, hast_ctx** out) {
                                 (int)sizeof(FusedSmem<false>)));                                                   \
     CU_NEW(cudaFuncSetAttribute(classify_kernel<KT, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                 (int)sizeof(FusedSmem<false>)));
-    HAST_ATTR(17) HAST_ATTR(21) HAST_ATTR(25) HAST_ATTR(31)
+    HAST_ATTR(21) HAST_ATTR(25) HAST_ATTR(31)
 #undef HAST_ATTR
     CU_NEW(cudaFuncSetAttribute(classify_kernel<0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(FusedSmem<false>)));

@@ -372,12 +372,13 @@ __device__ __forceinline__ void table_insert(const TableView& t, uint64_t canon,
     {   // pre-filter first: a key must never be in the table without its filter bits
         const FilterHash fh = filter_hash(canon);
         uint32_t word = fh.word;
+        unsigned long long bits = filter_bits(fh);
         if (t.filt_m) {                                    // minimizer-addressed filter (table.cuh)
             const uint64_t rc = revcomp_top(t.k < 32 ? (canon << (64 - 2 * t.k)) : canon, t.kmask);
             word = mini_word(minimizer_hash(canon, rc, t.k, (int)t.filt_m));
+            bits = mini_bits(mini_sel(canon, rc, t.k));
         }
         unsigned long long* fw = (unsigned long long*)(t.filt + (word >> t.filt_shift));
-        const unsigned long long bits = filter_bits(fh);
         if ((*(volatile unsigned long long*)fw & bits) != bits) atomicOr(fw, bits);
     }
     for (int d = 0; d <= kMaxDisp; ++d) {

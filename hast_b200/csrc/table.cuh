@@ -90,7 +90,19 @@ __host__ __device__ __forceinline__ uint64_t filter_bits(FilterHash f) {
 // Minimizer lengths: long enough that a human genome's minimizers far outnumber the filter words.
 constexpr uint32_t kMiniC = 0x9E3779B1u, kMiniD = 0x7F4A7C15u, kMiniC2 = 0x85EBCA77u;
 __host__ __device__ __forceinline__ constexpr int mini_len(int k) {
-    return (k == 21 || k == 25 || k == 31) ? 15 : k == 17 ? 13 : 0;      // 0: no minimizer sweep for this k
+    return (k == 21 || k == 25 || k == 31) ? 16 : 0;      // 0: no minimizer sweep for this k
+}
+// Bit selectors (5 + 5 bits) of a k-mer in the minimizer-addressed filter, k >= 16: a hash of the first and
+// last 16 bases of both strands that is symmetric in the strands, so the sweep needs neither the canonical
+// k-mer nor any 64-bit arithmetic (fwd / rc right-aligned, 2k bits)
+constexpr uint32_t kSelC1 = 0x27D4EB2Fu, kSelC2 = 0x165667B1u;
+__host__ __device__ __forceinline__ uint32_t mini_sel(uint64_t fwd, uint64_t rc, int k) {
+    const uint32_t ff = (uint32_t)(fwd >> (2 * k - 32)), fl = (uint32_t)fwd;
+    const uint32_t rf = (uint32_t)(rc >> (2 * k - 32)), rl = (uint32_t)rc;
+    return (ff * kSelC1 + fl * kSelC2 + rf * kSelC1 + rl * kSelC2) >> 22;
+}
+__host__ __device__ __forceinline__ uint64_t mini_bits(uint32_t sel) {
+    return (1ull << ((sel >> 5) & 31u)) | (1ull << (32u + (sel & 31u)));
 }
 __host__ __device__ __forceinline__ uint32_t mini_hash(uint32_t canon_mmer) { return canon_mmer * kMiniC + kMiniD; }
 // top bits pick the filter word (the minimum of several hashes is biased towards 0: remix it)

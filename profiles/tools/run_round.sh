@@ -8,7 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest_gpu.log
 tail -3 $O/${TAG}_pytest_gpu.log
 python bench.py --steps 5 --warmup 3 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.log; echo "bench rc=$?"
-python bench.py --workload cfg3t --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_cfg3t.json 2> $O/${TAG}_bench_cfg3t.log; echo "bench cfg3t rc=$?"
+python bench.py --workload cfg3t --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_cfg3t.json 2> $O/${TAG}_bench_cfg3t.log; echo "bench cfg3t rc=$?"
 python bench.py --impl reference --steps 1 --warmup 0 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.log; echo "ref rc=$?"
 KREG='regex:^(classify_kernel|tile_kernel|lookup_kernel|gather_kernel|table_)'
 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base function -k "$KREG" -c 400 --csv \
