@@ -59,6 +59,9 @@ constexpr int kFusedReadsPerTile = HAST_READS_PER_TILE;
 constexpr int kQueueCap = 6144;                          // passing positions buffered per CTA
 constexpr int kChunk = 16;                               // positions per thread per sweep (= bases per packed word)
 constexpr int kDrainUnroll = 4;                          // exact probes in flight per thread while draining
+constexpr int kWarpQueueCap = kQueueCap / 8;             // every warp of the CTA queues and drains on its own
+constexpr uint32_t kDrainChunk = 32u * kDrainUnroll;     // one full round of probes for a warp
+static_assert(kTileThreads == 8 * 32 && kWarpQueueCap >= (int)kDrainChunk - 1 + 16 * 32, "eight warps; a sweep appends up to 16 positions per lane");
 
 template <bool TMA>
 struct __align__(128) FusedSmem {
@@ -71,7 +74,7 @@ struct __align__(128) FusedSmem {
     uint32_t off[kFusedReadsPerTile + 1];
     uint32_t votes[kFusedReadsPerTile];
     unsigned long long mbar;                             // completion barrier of the bulk copy into raw
-    uint32_t qn;
+    uint32_t pad_;
 };
 static_assert(4 * (sizeof(FusedSmem<true>) + 1024) <= 227 * 1024, "four CTAs per SM must fit");
 static_assert(4 * (sizeof(FusedSmem<false>) + 1024) <= 227 * 1024, "four CTAs per SM must fit");
@@ -177,7 +180,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
     uint32_t* const s_packed = sm.packed;
     uint32_t* const s_bad = sm.bad;
     uint16_t* const s_queue = sm.queue;
-    uint32_t& s_qn = sm.qn;
+    uint16_t* const wqueue = s_queue + (threadIdx.x >> 5) * kWarpQueueCap;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const int k = KT ? KT : t.k;
@@ -206,7 +209,6 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
         else mbar_arrive(&sm.mbar);
     };
     uint32_t parity = 0;
-    if (tid == 0) s_qn = 0;
     if (TMA && tid == 0) {
         mbar_init(&sm.mbar, 1);
         const uint32_t r0 = blockIdx.x * kReadsPerTile;           // grid <= n_tiles: the first tile exists
@@ -371,6 +373,51 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
             }
             __syncthreads();
 
+            // (d) exact probe of queued positions [base, base + n) of this warp's queue, n <= kDrainChunk,
+            // kDrainUnroll probes in flight per lane
+            auto drain = [&](uint32_t base, uint32_t n) {
+                uint32_t p[kDrainUnroll];
+                uint64_t want[kDrainUnroll];
+                Bucket bk[kDrainUnroll];
+                uint32_t bucket[kDrainUnroll];
+                bool on[kDrainUnroll];
+#pragma unroll
+                for (int u = 0; u < kDrainUnroll; ++u) {
+                    const uint32_t i = u * 32u + lane;
+                    on[u] = i < n;
+                    p[u] = on[u] ? wqueue[base + i] : 0u;
+                }
+                __syncwarp();                              // the next append may overwrite these entries
+#pragma unroll
+                for (int u = 0; u < kDrainUnroll; ++u) {
+                    const uint64_t canon = canonical_at(s_packed, p[u], k, kmask);
+                    const uint64_t h = table_hash(canon, k, kmask);
+                    bucket[u] = (uint32_t)(h >> t.rem_bits);
+                    want[u] = (h & t.rem_mask) << 4;
+                    bk[u].s0 = bk[u].s1 = bk[u].s2 = bk[u].s3 = 0ull;
+                    if (on[u]) bk[u] = load_bucket(t.slots + (size_t)bucket[u] * kSlotsPerBucket);
+                }
+#pragma unroll
+                for (int u = 0; u < kDrainUnroll; ++u) {
+                    bool found;
+                    uint32_t tag = match_bucket(bk[u], want[u], found);
+                    if (on[u] && !found && (bk[u].s0 & 1ull)) {           // overflowed home bucket
+                        uint32_t bkt = bucket[u];
+                        uint64_t w = want[u];
+                        for (int d = 1; d <= kMaxDisp; ++d) {
+                            bkt = (bkt + 1) & t.bucket_mask;
+                            w += 1;
+                            const Bucket nb = load_bucket(t.slots + (size_t)bkt * kSlotsPerBucket);
+                            ++st_extra;
+                            tag = match_bucket(nb, w, found);
+                            if (found || !(nb.s0 & 1ull)) break;
+                        }
+                    }
+                    if (on[u] && tag) vote(s_votes, s_off, ra, rb, lo + p[u], tag);
+                }
+            };
+            uint32_t wq = 0;                               // entries in this warp's queue (same value in every lane)
+
             // (c) filter sweep: thread <-> packed word (16 positions)
             for (uint32_t wbase = 0; wbase < nseg; wbase += kTileThreads) {
                 const uint32_t wi = wbase + tid;
@@ -474,8 +521,10 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                     }
                     }
                 }
-                // append the passing positions to the queue: one shared atomic per warp; no
-                // CTA barrier between sweeps, the warps drift apart and overlap each other's loads
+                // append the passing positions to this WARP's queue (count kept in a register, no atomics), and
+                // as soon as it holds a full round of exact probes (kDrainUnroll per lane) drain that round:
+                // the warps of a CTA never wait for each other between sweeping and probing, and one warp's
+                // HBM latency is covered by the sweeps of the others
                 const uint32_t cnt = __popc(pass);
                 uint32_t incl = cnt;
 #pragma unroll
@@ -484,72 +533,27 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                     if (lane >= (uint32_t)o) incl += v;
                 }
                 const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                if (total) {
-                    uint32_t qbase = 0;
-                    if (lane == 31) qbase = atomicAdd(&s_qn, total);
-                    qbase = __shfl_sync(0xFFFFFFFFu, qbase, 31);
-                    uint32_t q = qbase + incl - cnt;
+                if (total) {                               // warp-uniform
+                    uint32_t q = wq + incl - cnt;
                     st_pass += cnt;
                     while (pass) {
                         const uint32_t j = __ffs(pass) - 1;
                         pass &= pass - 1;
-                        const uint32_t pos = wi * 16u + j;
-                        if (q < (uint32_t)kQueueCap) {
-                            s_queue[q] = (uint16_t)pos;
-                        } else {                           // queue full (saturated filter): resolve in place
-                            const uint32_t tag = table_probe(t, canonical_at(s_packed, pos, k, kmask), st_extra);
-                            if (tag) vote(s_votes, s_off, ra, rb, lo + pos, tag);
-                        }
-                        ++q;
+                        wqueue[q++] = (uint16_t)(wi * 16u + j);
+                    }
+                    wq += total;                           // < kDrainChunk + 512 <= kWarpQueueCap
+                    __syncwarp();
+                    while (wq >= kDrainChunk) {
+                        wq -= kDrainChunk;
+                        drain(wq, kDrainChunk);
                     }
                 }
             }
-            __syncthreads();
-
-            // (d) drain: exact probe of every queued position, four probes in flight per thread
-            {
-                const uint32_t qn = min(s_qn, (uint32_t)kQueueCap);
-                for (uint32_t i0 = (tid & ~31u) * kDrainUnroll; i0 < qn; i0 += kTileThreads * kDrainUnroll) {
-                    // this warp owns entries [i0, i0 + 32 * kDrainUnroll)
-                    uint32_t p[kDrainUnroll];
-                    uint64_t want[kDrainUnroll];
-                    Bucket bk[kDrainUnroll];
-                    uint32_t bucket[kDrainUnroll];
-                    bool on[kDrainUnroll];
-#pragma unroll
-                    for (int u = 0; u < kDrainUnroll; ++u) {
-                        const uint32_t i = i0 + u * 32u + lane;
-                        on[u] = i < qn;
-                        p[u] = on[u] ? s_queue[i] : 0u;
-                        const uint64_t canon = canonical_at(s_packed, p[u], k, kmask);
-                        const uint64_t h = table_hash(canon, k, kmask);
-                        bucket[u] = (uint32_t)(h >> t.rem_bits);
-                        want[u] = (h & t.rem_mask) << 4;
-                        bk[u].s0 = bk[u].s1 = bk[u].s2 = bk[u].s3 = 0ull;
-                        if (on[u]) bk[u] = load_bucket(t.slots + (size_t)bucket[u] * kSlotsPerBucket);
-                    }
-#pragma unroll
-                    for (int u = 0; u < kDrainUnroll; ++u) {
-                        bool found;
-                        uint32_t tag = match_bucket(bk[u], want[u], found);
-                        if (on[u] && !found && (bk[u].s0 & 1ull)) {       // overflowed home bucket
-                            uint32_t bkt = bucket[u];
-                            uint64_t w = want[u];
-                            for (int d = 1; d <= kMaxDisp; ++d) {
-                                bkt = (bkt + 1) & t.bucket_mask;
-                                w += 1;
-                                const Bucket nb = load_bucket(t.slots + (size_t)bkt * kSlotsPerBucket);
-                                ++st_extra;
-                                tag = match_bucket(nb, w, found);
-                                if (found || !(nb.s0 & 1ull)) break;
-                            }
-                        }
-                        if (on[u] && tag) vote(s_votes, s_off, ra, rb, lo + p[u], tag);
-                    }
-                }
+            if (wq) {                                      // warp-uniform
+                drain(0u, wq);
+                wq = 0;
             }
             __syncthreads();
-            if (tid == 0) s_qn = 0;                        // next append is behind the next pass's barriers
             ra = rb;
         }
 
