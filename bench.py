@@ -69,6 +69,8 @@ WORKLOAD_TEXT = {
     "cfg2": "configs[1]: synthetic 100 Mbp diploid trio (0.1% het), k=21, 20M stLFR 100bp read pairs / 500k barcodes",
     "cfg3t": "configs[2] table scale: human-size parent-unique k-mer lists (62 M keys: the cfg2 trio + random decoys), "
              "k=21, 20M stLFR 100bp read pairs / 500k barcodes per GPU",
+    "cfg3": "configs[2], the shard of one GPU out of eight: human-size parent-unique k-mer lists (62 M keys: the cfg2 trio + "
+            "random decoys), k=21, 75M stLFR 100bp read pairs (600M / 8) over 20M barcodes",
     "cfg1": "configs[0]: synthetic 5 Mbp diploid trio (0.1% het), k=21, 200k stLFR 100bp read pairs / 10k barcodes",
     "small": "dev: 500 kbp trio, 20k pairs / 1k barcodes",
 }
@@ -457,6 +459,7 @@ def main():
         h2d = n_reads * L + sum(b[4] + 1 for b in hb) * 4 + n_reads * 4
         e2e = {"value": world * P / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(nb * 8), "ms_per_step": dt * 1e3,
+               "h2d_gbs_per_gpu": h2d / dt / 1e9,        # against ~55 GB/s of a PCIe Gen5 x16 link: this leg is PCIe-bound
                "path": "hast_submit_batch (pinned host buffers, double-buffered cudaMemcpyAsync) + hast_finish"}
         del h_bases
 
@@ -511,6 +514,7 @@ def main():
                 + n_reads * 4
             e2e["packed"] = {"value": world * P / dtp, "unit": UNIT, "h2d_bytes_per_step": int(h2d_p),
                              "d2h_bytes_per_step": int(nb * 8), "ms_per_step": dtp * 1e3,
+                             "h2d_gbs_per_gpu": h2d_p / dtp / 1e9,
                              "path": "hast_submit_batch_packed: 2-bit words + containN bits as bin/classify's parser "
                                      "emits them by default (packing happens while parsing, outside this region)"}
             del pk_w, pk_f

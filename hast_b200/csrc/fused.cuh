@@ -55,13 +55,20 @@ namespace hast {
 #ifndef HAST_READS_PER_TILE
 #define HAST_READS_PER_TILE 240
 #endif
+#ifndef HAST_FUSED_THREADS
+#define HAST_FUSED_THREADS 256
+#endif
+#ifndef HAST_FUSED_CTAS_PER_SM
+#define HAST_FUSED_CTAS_PER_SM 4
+#endif
+constexpr int kFusedThreads = HAST_FUSED_THREADS;        // threads per CTA of classify_kernel
 constexpr int kFusedReadsPerTile = HAST_READS_PER_TILE;
-constexpr int kQueueCap = 6144;                          // passing positions buffered per CTA
+constexpr int kQueueCap = 768 * (HAST_FUSED_THREADS / 32);                          // passing positions buffered per CTA
 constexpr int kChunk = 16;                               // positions per thread per sweep (= bases per packed word)
 constexpr int kDrainUnroll = 4;                          // exact probes in flight per thread while draining
-constexpr int kWarpQueueCap = kQueueCap / 8;             // every warp of the CTA queues and drains on its own
+constexpr int kWarpQueueCap = kQueueCap / (kFusedThreads / 32);             // every warp of the CTA queues and drains on its own
 constexpr uint32_t kDrainChunk = 32u * kDrainUnroll;     // one full round of probes for a warp
-static_assert(kTileThreads == 8 * 32 && kWarpQueueCap >= (int)kDrainChunk - 1 + 16 * 32, "eight warps; a sweep appends up to 16 positions per lane");
+static_assert(kWarpQueueCap >= (int)kDrainChunk - 1 + 16 * 32, "eight warps; a sweep appends up to 16 positions per lane");
 
 template <bool TMA>
 struct __align__(128) FusedSmem {
@@ -76,8 +83,8 @@ struct __align__(128) FusedSmem {
     unsigned long long mbar;                             // completion barrier of the bulk copy into raw
     uint32_t pad_;
 };
-static_assert(4 * (sizeof(FusedSmem<true>) + 1024) <= 227 * 1024, "four CTAs per SM must fit");
-static_assert(4 * (sizeof(FusedSmem<false>) + 1024) <= 227 * 1024, "four CTAs per SM must fit");
+static_assert(HAST_FUSED_CTAS_PER_SM * (sizeof(FusedSmem<true>) + 1024) <= 227 * 1024, "the CTAs of an SM must fit");
+static_assert(HAST_FUSED_CTAS_PER_SM * (sizeof(FusedSmem<false>) + 1024) <= 227 * 1024, "the CTAs of an SM must fit");
 
 // hit at global base offset gp: add the tag bits to the vote word of the read that owns it,
 // s_off[r] <= gp < s_off[r+1] with r in [ra, rb)
@@ -167,7 +174,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 // sweep was bound by the one-divergent-request-per-clock limit of the L1 (profiles/r01_c); this trades
 // ~15 integer instructions per position for ~70 % of those requests.
 template <int KT, bool TMA, bool PACKED = false, bool SEQ = false, bool MINI = false>
-__global__ void __launch_bounds__(kTileThreads, 4)
+__global__ void __launch_bounds__(kFusedThreads, HAST_FUSED_CTAS_PER_SM)
 classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t n_barcodes,
                 DevStats* __restrict__ stats) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -220,8 +227,8 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t r0 = tile * kReadsPerTile;
         const uint32_t R = min((uint32_t)kReadsPerTile, b.n_reads - r0);
-        for (uint32_t i = tid; i <= R; i += kTileThreads) s_off[i] = b.read_off[r0 + i];
-        for (uint32_t i = tid; i < R; i += kTileThreads) s_votes[i] = 0;
+        for (uint32_t i = tid; i <= R; i += kFusedThreads) s_off[i] = b.read_off[r0 + i];
+        for (uint32_t i = tid; i < R; i += kFusedThreads) s_votes[i] = 0;
         // first pass of this CTA's next tile (thread 0 keeps its byte range in registers)
         const uint32_t ntile = tile + gridDim.x;
         uint32_t nt_lo = 0, nt_end = 0;
@@ -251,7 +258,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
             const uint32_t hi = too_long ? lo : s_off[rb];
             const uint32_t nseg = (hi - lo + 15u) >> 4;
 
-            for (uint32_t i = tid; i < (nseg >> 1) + 2; i += kTileThreads) s_bad[i] = 0;
+            for (uint32_t i = tid; i < (nseg >> 1) + 2; i += kFusedThreads) s_bad[i] = 0;
             if (TMA) {
                 mbar_wait(&sm.mbar, parity);               // this pass's bytes have landed in sm.raw
                 parity ^= 1u;
@@ -262,12 +269,12 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
             // are fetched before the first is packed, so a pass pays the DRAM latency of its ~10 segments
             // per thread three times instead of ten
             constexpr int kPackUnroll = 4;
-            for (uint32_t seg0 = tid; seg0 < nseg + 4; seg0 += kTileThreads * kPackUnroll) {
+            for (uint32_t seg0 = tid; seg0 < nseg + 4; seg0 += kFusedThreads * kPackUnroll) {
                 uint4 v[kPackUnroll];
                 bool full[kPackUnroll];
 #pragma unroll
                 for (int u = 0; u < kPackUnroll; ++u) {
-                    const uint32_t seg = seg0 + (uint32_t)u * kTileThreads;
+                    const uint32_t seg = seg0 + (uint32_t)u * kFusedThreads;
                     v[u] = make_uint4(0u, 0u, 0u, 0u);
                     full[u] = false;
                     if (seg >= nseg) continue;
@@ -287,7 +294,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                 }
 #pragma unroll
                 for (int u = 0; u < kPackUnroll; ++u) {
-                    const uint32_t seg = seg0 + (uint32_t)u * kTileThreads;
+                    const uint32_t seg = seg0 + (uint32_t)u * kFusedThreads;
                     if (seg >= nseg + 4) continue;
                     uint32_t word = 0;
                     if (PACKED) {
@@ -333,10 +340,10 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                 // a byte that is not ACGT spoils the k windows that contain it: smear every flag over
                 // the k-1 positions before it.  Read boundaries need no care, the last k-1 positions
                 // of a read start no k-mer anyway.
-                uint32_t smeared[(FusedSmem<TMA>::kWords / 2 + 2 + kTileThreads - 1) / kTileThreads];
+                uint32_t smeared[(FusedSmem<TMA>::kWords / 2 + 2 + kFusedThreads - 1) / kFusedThreads];
                 const uint32_t nbw = (nseg >> 1) + 1;
                 int it = 0;
-                for (uint32_t w = tid; w < nbw; w += kTileThreads, ++it) {
+                for (uint32_t w = tid; w < nbw; w += kFusedThreads, ++it) {
                     const uint64_t pair = (uint64_t)s_bad[w] | ((uint64_t)s_bad[w + 1] << 32);
                     uint64_t d = pair;
                     for (int j = 1; j < k; ++j) d |= pair >> j;
@@ -344,11 +351,11 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
                 }
                 __syncthreads();
                 it = 0;
-                for (uint32_t w = tid; w < nbw; w += kTileThreads, ++it) s_bad[w] = smeared[it];
+                for (uint32_t w = tid; w < nbw; w += kFusedThreads, ++it) s_bad[w] = smeared[it];
                 __syncthreads();
             }
             // (b) per read: containN (classify.cpp:182-185), positions that start no k-mer
-            for (uint32_t r = ra + tid; r < rb; r += kTileThreads) {
+            for (uint32_t r = ra + tid; r < rb; r += kFusedThreads) {
                 const uint32_t s = s_off[r] - lo, e = s_off[r + 1] - lo, L = e - s;
                 const bool has_n = SEQ ? false
                                  : PACKED ? ((b.has_n[(r0 + r) >> 5] >> ((r0 + r) & 31u)) & 1u) != 0u
@@ -419,7 +426,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
             uint32_t wq = 0;                               // entries in this warp's queue (same value in every lane)
 
             // (c) filter sweep: thread <-> packed word (16 positions)
-            for (uint32_t wbase = 0; wbase < nseg; wbase += kTileThreads) {
+            for (uint32_t wbase = 0; wbase < nseg; wbase += kFusedThreads) {
                 const uint32_t wi = wbase + tid;
                 uint32_t pass = 0;
                 uint32_t valid = 0;
@@ -558,7 +565,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
         }
 
         // (e) votes -> per-barcode counters (IncrBarcodeHaps, classify.cpp:203-206)
-        for (uint32_t rbase = 0; rbase < R; rbase += kTileThreads) {
+        for (uint32_t rbase = 0; rbase < R; rbase += kFusedThreads) {
             const uint32_t r = rbase + tid;
             const uint32_t v = r < R ? s_votes[r] : 0u;
             const unsigned voters = __ballot_sync(0xFFFFFFFFu, v != 0u);

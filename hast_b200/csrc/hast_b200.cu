@@ -179,21 +179,21 @@ int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv, uint64_t* d_kmers,
 #define HAST_LAUNCH_K(KT)                                                                                         \
     do {                                                                                                          \
         if (mini_len(KT) && ctx->tv.filt_m) {                                                                     \
-            if (bv.packed) classify_kernel<KT, false, true, false, mini_len(KT) != 0><<<fgrid, kTileThreads, sizeof(FusedSmem<false>), ctx->cs>>>( \
+            if (bv.packed) classify_kernel<KT, false, true, false, mini_len(KT) != 0><<<fgrid, kFusedThreads, sizeof(FusedSmem<false>), ctx->cs>>>( \
                     ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                               \
-            else classify_kernel<KT, false, false, false, mini_len(KT) != 0><<<fgrid, kTileThreads, sizeof(FusedSmem<false>), ctx->cs>>>( \
+            else classify_kernel<KT, false, false, false, mini_len(KT) != 0><<<fgrid, kFusedThreads, sizeof(FusedSmem<false>), ctx->cs>>>( \
                     ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                               \
         } else                                                                                                    \
-        if (bv.packed) classify_kernel<KT, false, true><<<fgrid, kTileThreads, sizeof(FusedSmem<false>), ctx->cs>>>( \
+        if (bv.packed) classify_kernel<KT, false, true><<<fgrid, kFusedThreads, sizeof(FusedSmem<false>), ctx->cs>>>( \
                 ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                                   \
-        else if (tma) classify_kernel<KT, true><<<fgrid, kTileThreads, sizeof(FusedSmem<true>), ctx->cs>>>(       \
+        else if (tma) classify_kernel<KT, true><<<fgrid, kFusedThreads, sizeof(FusedSmem<true>), ctx->cs>>>(       \
                 ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                                   \
-        else classify_kernel<KT, false><<<fgrid, kTileThreads, sizeof(FusedSmem<false>), ctx->cs>>>(              \
+        else classify_kernel<KT, false><<<fgrid, kFusedThreads, sizeof(FusedSmem<false>), ctx->cs>>>(              \
                 ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                                   \
     } while (0)
         if (ctx->opt_seq_mode) {
             if (bv.packed) return fail(ctx, HAST_E_STATE, "seq_mode takes ASCII batches");
-            classify_kernel<0, false, false, true><<<fgrid, kTileThreads, sizeof(FusedSmem<false>), ctx->cs>>>(
+            classify_kernel<0, false, false, true><<<fgrid, kFusedThreads, sizeof(FusedSmem<false>), ctx->cs>>>(
                 ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);
         } else
         switch (ctx->tv.k) {                      // specialised for HAST's default k and the benchmarked sweep
@@ -282,9 +282,9 @@ int hast_create(int device, hast_ctx** out) {
     CU_NEW(cudaFuncSetAttribute(classify_kernel<0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(FusedSmem<false>)));
     int per_sm_f = 0, per_sm_t = 0;
-    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, classify_kernel<0, false>, kTileThreads,
+    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, classify_kernel<0, false>, kFusedThreads,
                                                          sizeof(FusedSmem<false>)));
-    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, classify_kernel<0, true>, kTileThreads,
+    CU_NEW(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, classify_kernel<0, true>, kFusedThreads,
                                                          sizeof(FusedSmem<true>)));
     ctx->fused_blocks_tma = std::max(1, per_sm_t) * prop.multiProcessorCount;
 #undef CU_NEW

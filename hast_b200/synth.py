@@ -428,4 +428,11 @@ def config(name: str) -> TrioSpec:
         # (1 GiB) is HBM-resident and the pre-filter runs at its size cap
         return TrioSpec(genome_len=100_000_000, het=0.001, n_pairs=20_000_000, n_barcodes=500_000,
                         decoy_kmers=26_800_000)
+    if name == "cfg3":       # configs[2] as ONE GPU of eight sees it: human-size k-mer lists (as cfg3t), all 20 M barcodes,
+        # 600 M / 8 = 75 M read pairs (15 GB of bases, resident in HBM)
+        return TrioSpec(genome_len=100_000_000, het=0.001, n_pairs=75_000_000, n_barcodes=20_000_000,
+                        decoy_kmers=26_800_000)
+    if name == "cfg3b":      # configs[2] BARCODE scale for the test suite: 20 M barcodes (160 MB of counters, larger
+        # than L2), the cfg2 trio's own k-mer lists, 10 M pairs
+        return TrioSpec(genome_len=100_000_000, het=0.001, n_pairs=10_000_000, n_barcodes=20_000_000)
     raise KeyError(name)
