@@ -282,7 +282,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--table-scale", type=float, default=1.0, help="expected_keys multiplier (sparser table)")
-    ap.add_argument("--kernel", type=int, default=3, choices=[0, 1, 2, 3],
+    ap.add_argument("--kernel", type=int, default=3, choices=[0, 1, 2, 3, 4],
                     help="3 = pre-filtered fused kernel, filter word chosen by the k-mer's minimizer (default), "
                          "1 = filter word chosen by a hash of the k-mer, 2 = as 1 with TMA-staged reads, "
                          "0 = direct table probe per position")

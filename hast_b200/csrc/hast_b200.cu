@@ -173,13 +173,15 @@ int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv, uint64_t* d_kmers,
     const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->tile_blocks);
     if (mode == MODE_CLASSIFY && ctx->opt_kernel >= 1) {
         const uint32_t n_ftiles = (bv.n_reads + kFusedReadsPerTile - 1) / kFusedReadsPerTile;
-        const bool tma = ctx->opt_kernel == 2 && !bv.packed && !ctx->tv.filt_m;
+        const bool tma = (ctx->opt_kernel == 2 || ctx->opt_kernel == 4) && !bv.packed;
         const int fgrid = (int)std::min<uint32_t>(n_ftiles, (uint32_t)(tma ? ctx->fused_blocks_tma : ctx->fused_blocks));
         const uint32_t nbc = (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull);
 #define HAST_LAUNCH_K(KT)                                                                                         \
     do {                                                                                                          \
         if (mini_len(KT) && ctx->tv.filt_m) {                                                                     \
             if (bv.packed) classify_kernel<KT, false, true, false, mini_len(KT) != 0><<<fgrid, kFusedThreads, sizeof(FusedSmem<false>), ctx->cs>>>( \
+                    ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                               \
+            else if (tma) classify_kernel<KT, true, false, false, mini_len(KT) != 0><<<fgrid, kFusedThreads, sizeof(FusedSmem<true>), ctx->cs>>>( \
                     ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                               \
             else classify_kernel<KT, false, false, false, mini_len(KT) != 0><<<fgrid, kFusedThreads, sizeof(FusedSmem<false>), ctx->cs>>>( \
                     ctx->tv, bv, ctx->d_counts, nbc, ctx->d_stats);                                               \
@@ -276,7 +278,9 @@ int hast_create(int device, hast_ctx** out) {
     CU_NEW(cudaFuncSetAttribute(classify_kernel<KT, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)sizeof(FusedSmem<false>)));                                                   \
     CU_NEW(cudaFuncSetAttribute(classify_kernel<KT, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                (int)sizeof(FusedSmem<false>)));
+                                (int)sizeof(FusedSmem<false>)));                                                   \
+    CU_NEW(cudaFuncSetAttribute(classify_kernel<KT, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                (int)sizeof(FusedSmem<true>)));
     HAST_ATTR(21) HAST_ATTR(25) HAST_ATTR(31)
 #undef HAST_ATTR
     CU_NEW(cudaFuncSetAttribute(classify_kernel<0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -324,9 +328,9 @@ int hast_set_option(hast_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return fail(ctx, HAST_E_ARG, "NULL argument");
     const std::string n(name);
     if (n == "kernel") {
-        if (value < 0 || value > 3)
+        if (value < 0 || value > 4)
             return fail(ctx, HAST_E_ARG, "kernel: 0 (direct probe), 1 (pre-filter), 2 (pre-filter, TMA-staged reads), "
-                                         "3 (pre-filter addressed by minimizer)");
+                                         "3 (pre-filter addressed by minimizer), 4 (as 3, TMA-staged reads)");
         if (value == 0 && ctx->opt_seq_mode) return fail(ctx, HAST_E_STATE, "seq_mode needs the pre-filtered kernel");
         // the pre-filter of an existing table keeps its addressing scheme (tv.filt_m, which is what the launch
         // goes by): 1/2 <-> 3 takes effect at the next hast_table_begin
@@ -404,7 +408,7 @@ int hast_table_begin(hast_ctx* ctx, int k, uint64_t expected_keys) {
     ctx->tv.filt_shift = 32 - fb;
     // minimizer-addressed filter for the k-specialised sweeps (fused.cuh MINI); the stage-03 window rule and
     // the TMA variant run the generic sweep
-    ctx->tv.filt_m = (ctx->opt_kernel == 3 && !ctx->opt_seq_mode) ? (uint32_t)mini_len(k) : 0u;
+    ctx->tv.filt_m = (ctx->opt_kernel >= 3 && !ctx->opt_seq_mode) ? (uint32_t)mini_len(k) : 0u;
     CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->cs));
     if (ctx->d_counts) CU(cudaMemsetAsync(ctx->d_counts, 0, ctx->cap_barcodes * 2 * sizeof(int32_t), ctx->cs));
     ctx->table_ready = true;
@@ -756,7 +760,7 @@ int hast_finish(hast_ctx* ctx, int32_t* counts_out, uint64_t n_barcodes) {
                     std::to_string(ctx->tv.k) + " (the reference aborts on these, kmer.h:171)");
     if (ds.reads_too_long)
         return fail(ctx, HAST_E_ARG, std::to_string(ds.reads_too_long) + " read(s) longer than " +
-                    std::to_string((ctx->opt_kernel == 2 ? FusedSmem<true>::kCap : ctx->opt_kernel >= 1 ? FusedSmem<false>::kCap : kTileCapBytes) - 16) + " bases");
+                    std::to_string(((ctx->opt_kernel == 2 || ctx->opt_kernel == 4) ? FusedSmem<true>::kCap : ctx->opt_kernel >= 1 ? FusedSmem<false>::kCap : kTileCapBytes) - 16) + " bases");
     if (ds.bad_barcode)
         return fail(ctx, HAST_E_ARG, std::to_string(ds.bad_barcode) + " read(s) with barcode id >= reserved barcodes");
     if (n_barcodes > ctx->n_barcodes) return fail(ctx, HAST_E_ARG, "n_barcodes exceeds reserved barcodes");
