@@ -77,9 +77,9 @@ const char  *hast_last_error(const hast_ctx *ctx);      /* ctx may be NULL */
 int          hast_device(const hast_ctx *ctx);
 /* Tuning knobs, set before hast_table_begin: "kernel" (3 = pre-filtered fused
  * kernel whose filter word is chosen by the k-mer's minimizer, default for
- * k = 17/21/25/31; 1 = filter word chosen by a hash of the k-mer, what every
- * other k runs; 2 = as 1 with TMA-staged reads; 0 = direct table probe per
- * position; 1/2 <-> 3 takes effect at the next hast_table_begin), "filter_bits_per_key"
+ * k = 21/25/31; 1 = filter word chosen by a hash of the k-mer, what every
+ * other k runs; 2 / 4 = as 1 / 3 with TMA-staged reads; 0 = direct table probe per
+ * position; 1/2 <-> 3/4 takes effect at the next hast_table_begin), "filter_bits_per_key"
  * (default 16), "filter_max_bytes" (default 64 MiB: the filter is meant to stay
  * L2-resident).  None of them changes any result.  "seq_mode" = 1 switches the
  * fused kernel to the window rule of HAST stage 03 (03.mkoutput_by_fabulous2.0/
