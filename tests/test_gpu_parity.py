@@ -195,6 +195,42 @@ def test_long_reads_multi_pass(engine):
     assert (got == want).all() and st["lookups"] == lookups
 
 
+def test_very_long_reads_between_short_ones(engine):
+    """Reads of 5-24 kb (a shared-memory pass of their own, or most of one) mixed with ordinary ones, all cut from
+    one random genome so that the k-mer lists sampled from the short reads also hit inside the long ones."""
+    k = 21
+    rng = np.random.Generator(np.random.PCG64(77))
+    genome = cases.LET[rng.integers(0, 4, 60_000)].tobytes()
+    reads = []
+    for i in range(1500):
+        L = int(rng.integers(5_000, 24_001)) if i % 97 == 5 else int(rng.integers(k, 300))
+        s = int(rng.integers(0, len(genome) - L))
+        r = genome[s:s + L]
+        if rng.random() < 0.3:
+            r = cases.revcomp_ascii(r)
+        if i % 211 == 7:
+            r = r[:L // 2] + b"N" + r[L // 2 + 1:]
+        reads.append(r)
+    kmers = []
+    for _ in range(4000):
+        r = reads[int(rng.integers(0, len(reads)))]
+        if b"N" in r:
+            continue
+        p = int(rng.integers(0, len(r) - k + 1))
+        kmers.append(r[p:p + k])
+    half = len(kmers) // 2
+    case = dict(k=k, pat_text=b"".join(x + b"\n" for x in kmers[:half + 200]),
+                mat_text=b"".join(x + b"\n" for x in kmers[half - 200:]), reads=reads,
+                bc_ids=rng.integers(0, 23, len(reads)).astype(np.uint32), bc_names=[b"%d" % i for i in range(23)])
+    build_table(engine, case)
+    o, _ = build_oracle(case)
+    bases, off = cases.flatten(reads)
+    want, lookups = o.classify_batch(bases, off, case["bc_ids"], 23)
+    got, st = run_fused(engine, case, split=[500])
+    assert (got == want).all() and want.sum() > 1000
+    assert st["lookups"] == lookups and max(len(r) for r in reads) > 15_000
+
+
 def test_table_under_pressure(engine):
     """Overflowing buckets: displaced entries must still be found; a hopeless capacity is an error."""
     case = cases.adversarial_case(21, 4000, seed=12)
