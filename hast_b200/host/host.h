@@ -65,7 +65,9 @@ public:
     void export_names(std::vector<std::string>& out) const;
 private:
     struct Shard;
+    struct Arena;
     static constexpr int kShards = 256;
+    std::unique_ptr<Arena> arena_;                         // declared first: outlives the shards' tables
     std::unique_ptr<Shard[]> shards_;
     std::atomic<uint32_t> next_id_{0};
 };
@@ -94,10 +96,13 @@ struct Batch {
 
 // classify.cpp:112-119
 inline void parse_name(const char* head, size_t len, size_t& start, size_t& blen) {
+    // last '#' and last '/' of the header: the barcode sits at its end, so look from there
     long s = -1, e = -1;
-    for (size_t i = 0; i < len; ++i) {
-        if (head[i] == '#') s = (long)i;
-        if (head[i] == '/') e = (long)i;
+    for (size_t i = len; i-- > 0;) {
+        const char c = head[i];
+        if (c == '/' && e < 0) e = (long)i;
+        if (c == '#' && s < 0) s = (long)i;
+        if (s >= 0 && e >= 0) break;
     }
     long cnt = e - s - 1;
     start = (size_t)(s + 1);

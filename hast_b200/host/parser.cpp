@@ -9,6 +9,7 @@
 // hast_finish fails).
 #include <cstring>
 #include <immintrin.h>
+#include <vector>
 
 #include "host.h"
 
@@ -68,13 +69,54 @@ bool pack_append(const char* seq, size_t n, uint32_t* words, size_t& n_words, ui
     return has_n;
 }
 
+// Offsets of every '\n' of a block, found in one vector pass (the record loop below then walks this index
+// instead of calling memchr four times per record).
+__attribute__((target("avx2"))) static void newline_index_avx2(const char* p, size_t n, std::vector<uint32_t>& nl) {
+    const __m256i c = _mm256_set1_epi8('\n');
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + i));
+        uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, c));
+        while (m) {
+            nl.push_back((uint32_t)i + (uint32_t)__builtin_ctz(m));
+            m &= m - 1;
+        }
+    }
+    for (; i < n; ++i)
+        if (p[i] == '\n') nl.push_back((uint32_t)i);
+}
+static void newline_index(const char* p, size_t n, std::vector<uint32_t>& nl) {
+    nl.clear();
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) return newline_index_avx2(p, n, nl);
+    const __m128i c = _mm_set1_epi8('\n');
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p + i));
+        uint32_t m = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, c));
+        while (m) {
+            nl.push_back((uint32_t)i + (uint32_t)__builtin_ctz(m));
+            m &= m - 1;
+        }
+    }
+    for (; i < n; ++i)
+        if (p[i] == '\n') nl.push_back((uint32_t)i);
+}
+
 bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out) {
     const bool packed = out.packed != nullptr;
     size_t n_words = 0;
     uint64_t acc = 0;
     unsigned nbits = 0;
-    const char* p = blk.data.data();
+    const char* const base = blk.data.data();
+    const char* p = base;
     const char* const end = p + blk.len;
+    if (blk.len > 0xFFFFFFFFull) { out.error = "FASTQ block larger than 4 GiB"; return false; }
+    static thread_local std::vector<uint32_t> nl_index;   // one per parser thread, reused from block to block
+    newline_index(base, blk.len, nl_index);
+    const uint32_t* const nls = nl_index.data();
+    const size_t n_nl = nl_index.size();
+    size_t li = 0;                                        // next unused entry of nls: the newline that ends line li
     out.n_reads = 0;
     out.n_bases = 0;
     out.max_barcode = 0;
@@ -91,15 +133,14 @@ bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out) {
         out.barcode_id[r] = id;
     };
     while (p < end) {
-        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
-        if (!nl) break;                                   // unterminated header at EOF: dropped
+        if (li >= n_nl) break;                            // unterminated header at EOF: dropped
+        const char* nl = base + nls[li];
         const char* head = p;
         const size_t hlen = (size_t)(nl - p);
         p = nl + 1;
         const char* seq = p;
         size_t slen;
-        nl = p < end ? (const char*)memchr(p, '\n', (size_t)(end - p)) : nullptr;
-        if (nl) { slen = (size_t)(nl - p); p = nl + 1; }
+        if (li + 1 < n_nl) { nl = base + nls[li + 1]; slen = (size_t)(nl - p); p = nl + 1; }
         else { slen = (size_t)(end - p); p = end; }
         if (n >= out.cap_reads || nb + slen > (packed ? out.cap_words * 16 - 16 : out.cap_bases)) {
             out.error = "FASTQ records too small for the batch buffers (raise HAST_BLOCK_MB?)";
@@ -122,10 +163,8 @@ bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out) {
         out.read_off[n] = (uint32_t)nb;
         nb += slen;
         ++n;
-        for (int i = 0; i < 2 && p < end; ++i) {          // '+' line and quality line
-            nl = (const char*)memchr(p, '\n', (size_t)(end - p));
-            p = nl ? nl + 1 : end;
-        }
+        p = li + 3 < n_nl ? base + nls[li + 3] + 1 : end;    // past the '+' line and the quality line
+        li += 4;
     }
     for (uint32_t r = n >= kRing ? n - kRing : 0; r < n; ++r) resolve(r);
     if (packed && nbits) out.packed[n_words++] = (uint32_t)(acc << (32 - nbits));   // zero-padded last word
