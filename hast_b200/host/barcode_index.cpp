@@ -11,8 +11,10 @@
 // copy while the old one stays alive for the readers still probing it (they
 // can only miss, and a miss re-probes the current table under the shard lock).
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <sys/mman.h>
+#include <thread>
 
 #include "host.h"
 
@@ -192,13 +194,22 @@ uint32_t BarcodeIndex::intern_hashed(uint64_t h, const char* s, size_t n) {
 
 void BarcodeIndex::export_names(std::vector<std::string>& out) const {
     out.assign(size(), std::string());
-    for (int s = 0; s < kShards; ++s) {
-        const Table* t = shards_[s].cur.load(std::memory_order_acquire);
-        for (size_t i = 0; i <= t->mask; ++i) {
-            const Entry& e = t->slots[i];
-            if (e.hash.load(std::memory_order_acquire)) out[e.id].assign(e.data(), e.len);
+    // ids are unique, so the shards can be walked side by side (tens of millions of names at human scale)
+    const unsigned threads = out.size() < 200000 ? 1u : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        for (int s; (s = next.fetch_add(1)) < kShards;) {
+            const Table* t = shards_[s].cur.load(std::memory_order_acquire);
+            for (size_t i = 0; i <= t->mask; ++i) {
+                const Entry& e = t->slots[i];
+                if (e.hash.load(std::memory_order_acquire)) out[e.id].assign(e.data(), e.len);
+            }
         }
-    }
+    };
+    std::vector<std::thread> th;
+    for (unsigned i = 1; i < threads; ++i) th.emplace_back(work);
+    work();
+    for (auto& x : th) x.join();
 }
 
 }  // namespace hasthost
