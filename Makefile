@@ -44,7 +44,7 @@ bin/classify_seq: $(HOST)/classify_seq_main.cpp $(LIB) include/hast_b200.h
 	$(CXX) -O2 -g -std=c++17 -Wall -Iinclude $(HOST)/classify_seq_main.cpp -Lhast_b200/lib -lhast_b200 -lz \
 	    -Wl,-rpath,'$$ORIGIN/../hast_b200/lib' -o $@
 # stage 00's parent-unique k-mer lists from parental reads (count table on the GPU)
-bin/build_unshared_kmers: $(HOST)/build_unshared_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate.h $(LIB) include/hast_b200.h
+bin/build_unshared_kmers: $(HOST)/build_unshared_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate.h $(HOST)/crc32_clmul.h $(LIB) include/hast_b200.h
 	@mkdir -p bin
 	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(HOST)/build_unshared_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate_par.cpp -Lhast_b200/lib -lhast_b200 -lz \
 	    -Wl,-rpath,'$$ORIGIN/../hast_b200/lib' -o $@
@@ -53,7 +53,7 @@ bin/quartering_fastq: $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/
 	@mkdir -p bin
 	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/fastq_source.cpp $(HOST)/inflate.cpp $(HOST)/inflate_par.cpp -lz -o $@
 # the gzip decoder of the readers as a stand-alone tool (tests, timing)
-bin/hast_gunzip: $(HOST)/gunzip_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate_par.cpp $(HOST)/inflate.h $(HOST)/inflate_par.h
+bin/hast_gunzip: $(HOST)/gunzip_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate_par.cpp $(HOST)/inflate.h $(HOST)/crc32_clmul.h $(HOST)/inflate_par.h
 	@mkdir -p bin
 	$(CXX) -O2 -g -std=c++17 -Wall -pthread $(HOST)/gunzip_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate_par.cpp -lz -o $@
 bin/mergeResult: $(HOST)/merge_result_main.cpp

@@ -5,7 +5,9 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
-#include <zlib.h>          // crc32() only
+#include <zlib.h>          // crc32() only (crc32_clmul.h falls back to it)
+
+#include "crc32_clmul.h"
 
 #include <cerrno>
 #include <cstring>
@@ -527,7 +529,7 @@ bool GzipInflater::next(const uint8_t** data, size_t* len) {
     uint8_t* seg = chunk;                                         // start of the bytes not yet added to crc_ / member_out_
     auto account = [&] {
         if (out > seg) {
-            crc_ = (uint32_t)crc32(crc_, seg, (uInt)(out - seg));
+            crc_ = hast_crc32(crc_, seg, (size_t)(out - seg));
             member_out_ += (uint64_t)(out - seg);
         }
         seg = out;

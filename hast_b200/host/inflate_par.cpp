@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "crc32_clmul.h"
 #include "inflate.h"
 
 namespace hasthost {
@@ -634,7 +635,7 @@ void ParallelGzip::run() {
                 for (size_t p = sg.begin; p < sg.end;) {
                     const size_t m = std::min<size_t>(sg.end - p, 65536);
                     resolve_symbols(sym + p, m, w, dst + p);
-                    crc = (uint32_t)crc32(crc, dst + p, (uInt)m);
+                    crc = hast_crc32(crc, dst + p, m);
                     p += m;
                 }
                 sg.crc_got = crc;
