@@ -483,7 +483,7 @@ int main(int argc, char** argv) {
                 std::vector<std::thread> readers;
                 q_full.reopen();
                 const int n_readers = left;
-                int inflate_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2u / (unsigned)std::max(n_readers, 1)));
+                int inflate_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() * 3u / 4u / (unsigned)std::max(n_readers, 1)));
                 if (const char* e = getenv("HAST_INFLATE_THREADS")) inflate_threads = std::max(1, atoi(e));
                 for (int r = 0; r < n_readers; ++r)
                     readers.emplace_back([&] {

@@ -244,8 +244,10 @@ int run_classify(const Options& opt, RunStats& st) {
     std::atomic<uint64_t> text_bytes{0};
     std::atomic<size_t> next_file{0};
     const int n_readers = (int)std::max<size_t>(1, std::min<size_t>({opt.reads.size(), (size_t)opt.threads, (size_t)8}));
-    // threads per gzip stream (inflate_par.h): half the cores go to inflating, shared by the files read at once
-    int inflate_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2u / (unsigned)n_readers));
+    // threads per gzip stream (inflate_par.h)
+    // decoding one gzip stream on several threads costs ~2.5x the parser's CPU per byte: three
+    // quarters of the cores go to the decoders, shared by the files read side by side
+    int inflate_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() * 3u / 4u / (unsigned)n_readers));
     if (const char* e = getenv("HAST_INFLATE_THREADS")) inflate_threads = std::max(1, atoi(e));
     std::atomic<int> readers_left{n_readers};
     std::vector<std::thread> readers;
