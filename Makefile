@@ -25,10 +25,17 @@ $(LIB): $(CSRC)/hast_b200.cu $(CSRC)/kcount.cuh $(CSRC)/kernels.cuh $(CSRC)/fuse
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared $< -o $@ -ldl 2> hast_b200/lib/ptxas.log || (cat hast_b200/lib/ptxas.log; exit 1)
 	@grep -E "registers|spill" hast_b200/lib/ptxas.log | sort | uniq -c | sort -rn | head -20 || true
 
-tools: $(TOOLS)
-$(TOOLS): hast_b200/tools/fastq_fmt.c
+# synthetic-data helpers (FASTQ text emitter, counter-based read-pair generator: host and device builds)
+SYNTH_CUDA := hast_b200/lib/libhast_synth_cuda.so
+tools: $(TOOLS) $(SYNTH_CUDA)
+$(TOOLS): hast_b200/tools/fastq_fmt.c hast_b200/tools/synth_gen_cpu.cpp hast_b200/tools/synth_gen.h
 	@mkdir -p hast_b200/lib
-	$(CC) -O2 -std=c11 -fPIC -shared $< -lz -o $@
+	$(CC) -O2 -std=c11 -fPIC -c hast_b200/tools/fastq_fmt.c -o hast_b200/lib/fastq_fmt.o
+	$(CXX) -O2 -std=c++17 -fPIC -pthread -shared hast_b200/tools/synth_gen_cpu.cpp hast_b200/lib/fastq_fmt.o -lz -o $@
+	@rm -f hast_b200/lib/fastq_fmt.o
+$(SYNTH_CUDA): hast_b200/tools/synth_gen.cu hast_b200/tools/synth_gen.h
+	@mkdir -p hast_b200/lib
+	$(NVCC) $(NVFLAGS) -shared $< -o $@
 
 host: bin/classify bin/mergeResult bin/quartering_fastq bin/classify_seq bin/build_unshared_kmers bin/hast_gunzip
 HOST_SRCS := $(wildcard $(HOST)/*.cpp)

@@ -140,6 +140,8 @@ def _tools():
     lib.ff_write_fastq.restype = C.c_int
     lib.ff_write_fastq.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.ff_append_fastq.restype = C.c_int
+    lib.ff_append_fastq.argtypes = lib.ff_write_fastq.argtypes
     return lib
 
 
