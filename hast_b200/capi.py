@@ -38,7 +38,8 @@ class TableInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("batches", "reads", "bases", "lookups", "reads_with_n", "reads_short",
-                 "extra_probes", "kernel_launches", "h2d_bytes", "d2h_bytes", "filter_pass", "filter_loads")]
+                 "extra_probes", "kernel_launches", "h2d_bytes", "d2h_bytes", "filter_pass", "filter_loads",
+                 "finish_reduce_us", "finish_d2h_us")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -87,6 +87,7 @@ struct hast_ctx {
     cudaStream_t cs = nullptr;            // compute stream
     cudaStream_t hs = nullptr;            // host-to-device copy stream
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEvent_t f0 = nullptr, f1 = nullptr;   // hast_finish: reduce / read-back timing
 
     TableView tv{};
     uint64_t n_buckets = 0;
@@ -113,7 +114,8 @@ struct hast_ctx {
     int fused_blocks = 0, fused_blocks_tma = 0;   // persistent grids of classify_kernel<*, false / true>
     uint64_t filt_words = 0;
     // options (hast_set_option)
-    int64_t opt_kernel = 3;               // 3 = classify_kernel with the minimizer-addressed pre-filter (k = 17/21/25/31; other k run as 1),
+    int64_t opt_kernel = 3;               // 3 = classify_kernel with the minimizer-addressed pre-filter (k = 21/25/31, the k with
+                                          // mini_len(k) != 0 in table.cuh; every other k -- 17 included -- runs as 1), 4 = as 3 with TMA-staged reads,
                                           // 1 = classify_kernel (per-k-mer filter word), 2 = same with TMA-staged reads, 0 = tile_kernel<MODE_CLASSIFY>
     int64_t opt_seq_mode = 0;             // 1 = stage-03 window rule (classify_kernel<.., SEQ>)
     int64_t opt_filter_bits_per_key = 16;
@@ -254,6 +256,8 @@ int hast_create(int device, hast_ctx** out) {
     CU_NEW(cudaStreamCreateWithFlags(&ctx->hs, cudaStreamNonBlocking));
     CU_NEW(cudaEventCreate(&ctx->t0));
     CU_NEW(cudaEventCreate(&ctx->t1));
+    CU_NEW(cudaEventCreate(&ctx->f0));
+    CU_NEW(cudaEventCreate(&ctx->f1));
     for (auto& s : ctx->slot) {
         CU_NEW(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
         CU_NEW(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -319,6 +323,8 @@ void hast_destroy(hast_ctx* ctx) {
     cudaFree(ctx->d_kc_stats);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->f0) cudaEventDestroy(ctx->f0);
+    if (ctx->f1) cudaEventDestroy(ctx->f1);
     if (ctx->cs) cudaStreamDestroy(ctx->cs);
     if (ctx->hs) cudaStreamDestroy(ctx->hs);
     delete ctx;
@@ -406,8 +412,8 @@ int hast_table_begin(hast_ctx* ctx, int k, uint64_t expected_keys) {
     CU(cudaMalloc(&ctx->tv.filt, ctx->filt_words * 8));
     CU(cudaMemsetAsync(ctx->tv.filt, 0, ctx->filt_words * 8, ctx->cs));
     ctx->tv.filt_shift = 32 - fb;
-    // minimizer-addressed filter for the k-specialised sweeps (fused.cuh MINI); the stage-03 window rule and
-    // the TMA variant run the generic sweep
+    // minimizer-addressed filter for the k with a MINI sweep (fused.cuh; kernel 3 and its TMA-staged form 4);
+    // the stage-03 window rule, kernels 1/2 and every other k use the per-k-mer filter word
     ctx->tv.filt_m = (ctx->opt_kernel >= 3 && !ctx->opt_seq_mode) ? (uint32_t)mini_len(k) : 0u;
     CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->cs));
     if (ctx->d_counts) CU(cudaMemsetAsync(ctx->d_counts, 0, ctx->cap_barcodes * 2 * sizeof(int32_t), ctx->cs));
@@ -535,6 +541,12 @@ int hast_table_clone(hast_ctx* dst, hast_ctx* src) {
     hast_ctx* ctx = dst;
     if (!dst || !src) return fail(dst, HAST_E_ARG, "NULL context");
     if (!src->table_ready) return fail(dst, HAST_E_STATE, "source table not built");
+    // the filter layout must match the kernel the destination will launch (hast_set_option guards a
+    // context's own table the same way)
+    if (dst->opt_seq_mode && src->tv.filt_m)
+        return fail(dst, HAST_E_STATE, "hast_table_clone: the source pre-filter is minimizer-addressed, the destination is in seq_mode");
+    if (dst->opt_kernel == 0 && src->opt_seq_mode)
+        return fail(dst, HAST_E_STATE, "hast_table_clone: a seq_mode table needs the pre-filtered kernel");
     CU(cudaSetDevice(src->device));
     CU(cudaStreamSynchronize(src->cs));
     CU(cudaSetDevice(dst->device));
@@ -765,6 +777,7 @@ int hast_finish(hast_ctx* ctx, int32_t* counts_out, uint64_t n_barcodes) {
         return fail(ctx, HAST_E_ARG, std::to_string(ds.bad_barcode) + " read(s) with barcode id >= reserved barcodes");
     if (n_barcodes > ctx->n_barcodes) return fail(ctx, HAST_E_ARG, "n_barcodes exceeds reserved barcodes");
     const int32_t* src = ctx->d_counts;
+    float ms = 0.f;
     if (ctx->comm) {
         if (n_barcodes > ctx->cap_reduced) {
             if (ctx->d_reduced) CU(cudaFree(ctx->d_reduced));
@@ -772,13 +785,21 @@ int hast_finish(hast_ctx* ctx, int32_t* counts_out, uint64_t n_barcodes) {
             ctx->cap_reduced = n_barcodes;
         }
         // BarcodeCache::Add (classify.cpp:57-63) across GPUs: one int32 sum to rank 0
+        CU(cudaEventRecord(ctx->f0, ctx->cs));
         NC(g_nccl.Reduce(ctx->d_counts, ctx->d_reduced, n_barcodes * 2, ncclInt32, ncclSum, 0, ctx->comm, ctx->cs));
+        CU(cudaEventRecord(ctx->f1, ctx->cs));
         CU(cudaStreamSynchronize(ctx->cs));
+        CU(cudaEventElapsedTime(&ms, ctx->f0, ctx->f1));
+        ctx->st.finish_reduce_us += (uint64_t)(ms * 1000.f);
         src = ctx->d_reduced;
     }
     if (counts_out && n_barcodes && ctx->rank == 0) {
+        CU(cudaEventRecord(ctx->f0, ctx->cs));
         CU(cudaMemcpyAsync(counts_out, src, n_barcodes * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cs));
+        CU(cudaEventRecord(ctx->f1, ctx->cs));
         CU(cudaStreamSynchronize(ctx->cs));
+        CU(cudaEventElapsedTime(&ms, ctx->f0, ctx->f1));
+        ctx->st.finish_d2h_us += (uint64_t)(ms * 1000.f);
         ctx->st.d2h_bytes += n_barcodes * 2 * sizeof(int32_t);
     }
     return HAST_OK;

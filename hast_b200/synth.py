@@ -120,15 +120,15 @@ class Trio:
         off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
         read_no = np.arange(lo, hi, dtype=np.uint64)
         bc = np.ascontiguousarray(self.pair_bc[lo:hi], dtype=np.uint32)
-        lib = _tools()
         paths = []
+        CH = 1 << 21
         for mate, arr in ((1, self.r1), (2, self.r2)):
-            seqs = np.ascontiguousarray(self._np(arr[lo:hi])).reshape(-1)
             p = str(outdir / f"{stem}.r{mate}.fq{'.gz' if gz else ''}")
-            rc = lib.ff_write_fastq(p.encode(), int(gz), seqs.ctypes.data, off.ctypes.data, n, blob,
-                                    name_off.ctypes.data, bc.ctypes.data, read_no.ctypes.data, mate)
-            if rc:
-                raise OSError(f"cannot write {p}")
+            with FastqWriter(p, (6 if gz is True else int(gz)) if gz else 0) as w:
+                for a in range(0, n, CH):
+                    b = min(n, a + CH)
+                    seqs = np.ascontiguousarray(self._np(arr[lo + a:lo + b])).reshape(-1)
+                    w.add(seqs, off[:b - a + 1], blob, name_off, bc[a:b], read_no[a:b], mate)
             paths.append(p)
         return tuple(paths)
 
@@ -140,9 +140,49 @@ def _tools():
     lib.ff_write_fastq.restype = C.c_int
     lib.ff_write_fastq.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-    lib.ff_append_fastq.restype = C.c_int
-    lib.ff_append_fastq.argtypes = lib.ff_write_fastq.argtypes
+    lib.ff_open.restype = C.c_void_p
+    lib.ff_open.argtypes = [C.c_char_p, C.c_int]
+    lib.ff_add.restype = C.c_int
+    lib.ff_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_void_p,
+                           C.c_void_p, C.c_int]
+    lib.ff_close.restype = C.c_int
+    lib.ff_close.argtypes = [C.c_void_p]
     return lib
+
+
+class FastqWriter:
+    """Multi-threaded FASTQ writer of the synthetic generators (tools/fastq_fmt.c ff_open/ff_add/ff_close): plain text,
+    or -- gz_level 1..9 -- ONE gzip member deflated on all cores."""
+
+    def __init__(self, path, gz_level: int = 0):
+        self.lib = _tools()
+        self.path = str(path)
+        self.h = self.lib.ff_open(self.path.encode(), int(gz_level))
+        if not self.h:
+            raise OSError(f"cannot write {path}")
+
+    def add(self, seqs: np.ndarray, off: np.ndarray, blob: bytes, name_off: np.ndarray, bc: np.ndarray,
+            read_no: np.ndarray, mate: int):
+        seqs = np.ascontiguousarray(seqs, np.uint8).reshape(-1)
+        off = np.ascontiguousarray(off, np.uint64)
+        bc = np.ascontiguousarray(bc, np.uint32)
+        read_no = np.ascontiguousarray(read_no, np.uint64)
+        name_off = np.ascontiguousarray(name_off, np.uint64)
+        if self.lib.ff_add(self.h, seqs.ctypes.data, off.ctypes.data, bc.size, blob, name_off.ctypes.data,
+                           bc.ctypes.data, read_no.ctypes.data, mate):
+            raise OSError(f"cannot write {self.path}")
+
+    def close(self):
+        if self.h:
+            h, self.h = self.h, None
+            if self.lib.ff_close(h):
+                raise OSError(f"cannot write {self.path}")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 # --------------------------------------------------------------------------

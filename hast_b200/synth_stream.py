@@ -334,32 +334,26 @@ class StreamTrio:
     def write_fastq(self, outdir, pair_idx=None, lo: int = 0, hi: int | None = None, gz: bool = False,
                     stem: str = "child", chunk: int = 1 << 21, names=None):
         """child.r1.fq[.gz] / child.r2.fq[.gz] of pairs [lo, hi) or of the listed pair indices."""
-        from .synth import _tools
+        from .synth import FastqWriter
         outdir = Path(outdir)
         outdir.mkdir(parents=True, exist_ok=True)
         blob, name_off = names if names is not None else self.barcode_name_blob()
         L = self.spec.read_len
-        lib = _tools()
         paths = [str(outdir / f"{stem}.r{m}.fq{'.gz' if gz else ''}") for m in (1, 2)]
-        for p in paths:
-            open(p, "wb").close()
+        level = (6 if gz is True else int(gz)) if gz else 0
         if pair_idx is None:
             hi = self.spec.n_pairs if hi is None else hi
             pieces = ((np.arange(a, min(hi, a + chunk), dtype=np.uint64)) for a in range(lo, hi, chunk))
         else:
             pair_idx = np.asarray(pair_idx, dtype=np.uint64)
             pieces = (pair_idx[a:a + chunk] for a in range(0, pair_idx.size, chunk))
-        for idx in pieces:
-            m = idx.size
-            if not m:
-                continue
-            bases, bc = self.gen_pairs_idx(idx.astype(np.int64))
-            off = np.arange(m + 1, dtype=np.uint64) * np.uint64(L)
-            for mate, path in ((1, paths[0]), (2, paths[1])):
-                seqs = np.ascontiguousarray(bases[(mate - 1) * m: mate * m]).reshape(-1)
-                rc = lib.ff_append_fastq(path.encode(), int(gz), seqs.ctypes.data, off.ctypes.data, m, blob,
-                                         name_off.ctypes.data, np.ascontiguousarray(bc[:m]).ctypes.data,
-                                         np.ascontiguousarray(idx).ctypes.data, mate)
-                if rc:
-                    raise OSError(f"cannot write {path}")
+        with FastqWriter(paths[0], level) as w1, FastqWriter(paths[1], level) as w2:
+            for idx in pieces:
+                m = idx.size
+                if not m:
+                    continue
+                bases, bc = self.gen_pairs_idx(idx.astype(np.int64))
+                off = np.arange(m + 1, dtype=np.uint64) * np.uint64(L)
+                w1.add(bases[:m], off, blob, name_off, bc[:m], idx, 1)
+                w2.add(bases[m:], off, blob, name_off, bc[:m], idx, 2)
         return tuple(paths)

@@ -44,19 +44,23 @@ int ff_write_fastq(const char *path, int gz, const uint8_t *seqs, const uint64_t
     return 0;
 }
 
-/* ---- appending, multi-threaded variant (large synthetic files) ----------------------------------------
- * Appends reads to `path`.  The n reads are cut into one range per thread; each range is formatted and,
- * when gz_level > 0, deflated into its own gzip member in memory; the pieces are then appended in order.
- * A file of concatenated members is what `cat a.gz b.gz` or bgzip produce; zlib's gzread (the
- * reference's igzstream) walks them transparently.                                                      */
+/* ---- multi-threaded writer (large synthetic files) -------------------------------------------------------
+ * ff_open / ff_add / ff_close.  Each ff_add cuts its n reads into one range per thread; every range is
+ * formatted and, when gz_level > 0, deflated on its own thread into raw DEFLATE blocks that end on a byte
+ * boundary (Z_FULL_FLUSH), pigz-style; the pieces are written in order, so the file is ONE gzip member -- what
+ * a sequencer ships and the hard case for a parallel decoder (no member or flush-point index to lean on:
+ * block boundaries are not byte aligned in general, these happen to be every few tens of MB only).
+ * CRC-32 of the member = crc32_combine over the pieces.                                                      */
 #include <pthread.h>
 #include <unistd.h>
+
+typedef struct { FILE *f; int level; uLong crc; uint64_t isize; } ff_writer;
 
 typedef struct {
     const uint8_t *seqs; const uint64_t *off; size_t lo, hi;
     const char *bc_names; const uint64_t *bc_name_off; const uint32_t *bc_id; const uint64_t *read_no;
     int mate, gz_level;
-    char *out; size_t out_len; int err;
+    char *out; size_t out_len; uLong crc; size_t text_len; int err;
 } ff_job;
 
 static void *ff_job_run(void *arg) {
@@ -75,55 +79,96 @@ static void *ff_job_run(void *arg) {
         memset(buf + len, 'F', L); len += L;
         buf[len++] = '\n';
     }
+    j->text_len = len;
     if (!j->gz_level) { j->out = buf; j->out_len = len; return NULL; }
+    uLong crc = crc32(0L, Z_NULL, 0);
+    for (size_t p = 0; p < len; p += (1u << 30)) crc = crc32(crc, (const Bytef *)buf + p, (uInt)(len - p > (1u << 30) ? (1u << 30) : len - p));
+    j->crc = crc;
     z_stream z;
     memset(&z, 0, sizeof z);
-    if (deflateInit2(&z, j->gz_level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) { free(buf); j->err = 1; return NULL; }
-    size_t zcap = deflateBound(&z, (uLong)len) + 64;
+    if (deflateInit2(&z, j->gz_level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { free(buf); j->err = 1; return NULL; }
+    size_t zcap = len + len / 8 + 4096;
     char *zb = (char *)malloc(zcap);
     if (!zb) { deflateEnd(&z); free(buf); j->err = 1; return NULL; }
-    size_t in_done = 0;
-    z.next_out = (Bytef *)zb;
-    size_t out_left = zcap;
-    int rc = Z_OK;
-    while (rc != Z_STREAM_END) {                                /* zlib counts in 32 bits: feed in slices */
+    size_t in_done = 0, out_done = 0;
+    for (;;) {                                                   /* zlib counts in 32 bits: feed in slices */
         size_t in_now = len - in_done; if (in_now > (1u << 30)) in_now = 1u << 30;
-        size_t out_now = out_left > (1u << 30) ? (1u << 30) : out_left;
-        z.next_in = (Bytef *)(buf + in_done); z.avail_in = (uInt)in_now; z.avail_out = (uInt)out_now;
-        rc = deflate(&z, in_done + in_now == len ? Z_FINISH : Z_NO_FLUSH);
-        if (rc != Z_OK && rc != Z_STREAM_END && rc != Z_BUF_ERROR) { j->err = 1; break; }
+        size_t out_now = zcap - out_done; if (out_now > (1u << 30)) out_now = 1u << 30;
+        const int last = in_done + in_now == len;
+        z.next_in = (Bytef *)(buf + in_done); z.avail_in = (uInt)in_now;
+        z.next_out = (Bytef *)(zb + out_done); z.avail_out = (uInt)out_now;
+        int rc = deflate(&z, last ? Z_FULL_FLUSH : Z_NO_FLUSH);
+        if (rc != Z_OK && rc != Z_BUF_ERROR) { j->err = 1; break; }
         in_done += in_now - z.avail_in;
-        out_left -= out_now - z.avail_out;
+        out_done += out_now - z.avail_out;
+        if (last && z.avail_in == 0 && z.avail_out != 0) break;
+        if (out_done == zcap) { j->err = 1; break; }
     }
-    j->out_len = zcap - out_left;
+    j->out_len = out_done;
     j->out = zb;
     deflateEnd(&z);
     free(buf);
     return NULL;
 }
 
-int ff_append_fastq(const char *path, int gz_level, const uint8_t *seqs, const uint64_t *off, size_t n,
-                    const char *bc_names, const uint64_t *bc_name_off, const uint32_t *bc_id,
-                    const uint64_t *read_no, int mate) {
+void *ff_open(const char *path, int gz_level) {
+    ff_writer *w = (ff_writer *)calloc(1, sizeof *w);
+    if (!w) return NULL;
+    w->f = fopen(path, "wb");
+    if (!w->f) { free(w); return NULL; }
+    w->level = gz_level;
+    w->crc = crc32(0L, Z_NULL, 0);
+    if (gz_level) {
+        static const unsigned char hdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3};
+        fwrite(hdr, 1, 10, w->f);
+    }
+    return w;
+}
+
+int ff_add(void *handle, const uint8_t *seqs, const uint64_t *off, size_t n, const char *bc_names,
+           const uint64_t *bc_name_off, const uint32_t *bc_id, const uint64_t *read_no, int mate) {
+    ff_writer *w = (ff_writer *)handle;
+    if (!w || !w->f) return -1;
     long hw = sysconf(_SC_NPROCESSORS_ONLN);
     size_t t = (size_t)(hw > 0 ? hw : 1);
     if (t > 64) t = 64;
     if (t > n / 4096 + 1) t = n / 4096 + 1;
     ff_job jobs[64];
     pthread_t th[64];
+    int started[64];
     for (size_t i = 0; i < t; i++) {
-        ff_job j = {seqs, off, n * i / t, n * (i + 1) / t, bc_names, bc_name_off, bc_id, read_no, mate, gz_level, NULL, 0, 0};
+        ff_job j = {seqs, off, n * i / t, n * (i + 1) / t, bc_names, bc_name_off, bc_id, read_no, mate, w->level, NULL, 0, 0, 0, 0};
         jobs[i] = j;
-        if (pthread_create(&th[i], NULL, ff_job_run, &jobs[i])) { ff_job_run(&jobs[i]); th[i] = 0; }
+        started[i] = pthread_create(&th[i], NULL, ff_job_run, &jobs[i]) == 0;
+        if (!started[i]) ff_job_run(&jobs[i]);
     }
-    FILE *f = fopen(path, "ab");
-    int err = f ? 0 : -1;
+    int err = 0;
     for (size_t i = 0; i < t; i++) {
-        if (th[i]) pthread_join(th[i], NULL);
+        if (started[i]) pthread_join(th[i], NULL);
         if (jobs[i].err) err = -1;
-        if (!err && jobs[i].out_len && fwrite(jobs[i].out, 1, jobs[i].out_len, f) != jobs[i].out_len) err = -1;
+        if (!err && jobs[i].out_len && fwrite(jobs[i].out, 1, jobs[i].out_len, w->f) != jobs[i].out_len) err = -1;
+        if (!err && w->level) {
+            size_t left = jobs[i].text_len;                       /* crc32_combine takes a z_off_t length */
+            uLong c = jobs[i].crc;
+            (void)left;
+            w->crc = crc32_combine(w->crc, c, (z_off_t)jobs[i].text_len);
+            w->isize += jobs[i].text_len;
+        }
         free(jobs[i].out);
     }
-    if (f) fclose(f);
+    return err;
+}
+
+int ff_close(void *handle) {
+    ff_writer *w = (ff_writer *)handle;
+    if (!w) return -1;
+    int err = 0;
+    if (w->f && w->level) {
+        unsigned char tail[10] = {0x03, 0x00, 0, 0, 0, 0, 0, 0, 0, 0};   /* final empty fixed block, CRC-32, ISIZE */
+        for (int i = 0; i < 4; i++) { tail[2 + i] = (unsigned char)(w->crc >> (8 * i)); tail[6 + i] = (unsigned char)(w->isize >> (8 * i)); }
+        if (fwrite(tail, 1, 10, w->f) != 10) err = -1;
+    }
+    if (w->f && fclose(w->f)) err = -1;
+    free(w);
     return err;
 }

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HAST_ABI_VERSION 4
+#define HAST_ABI_VERSION 5
 
 #define HAST_OK            0
 #define HAST_E_ARG        -1   /* bad argument                                            */
@@ -65,6 +65,8 @@ typedef struct hast_stats {
     uint64_t d2h_bytes;
     uint64_t filter_pass;      /* lookups the pre-filter sent on to the exact table       */
     uint64_t filter_loads;     /* 8-byte pre-filter words fetched (minimizer sweep: < lookups) */
+    uint64_t finish_reduce_us; /* hast_finish: the ncclReduce of the counts, CUDA-event time (cumulative) */
+    uint64_t finish_d2h_us;    /* hast_finish: the read-back of the counts to the host (cumulative)        */
 } hast_stats;
 
 /* ---- library / context ------------------------------------------------- */

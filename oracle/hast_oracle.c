@@ -307,6 +307,20 @@ long ho_load_kmers_mem(ho_classifier *c, const char *text, size_t n, int index) 
     return total;
 }
 
+/* Harness convenience for the large configurations (not a reference function): the k-mers of a list that the
+ * generator already holds as packed words of the reference's code (kmer.h:11-12, first base in the highest used
+ * bits), inserted exactly as load_kmers does after str2Kmer -- canonical form (kmer.h:153-166), then the set. */
+long ho_load_kmers_packed(ho_classifier *c, const uint64_t *kmers, size_t n, int k, int index) {
+    if (k < 1 || k > 32) { snprintf(c->err, sizeof c->err, "k=%d outside 1..32", k); return -1; }
+    if (index == 0) c->k = k;
+    else if (c->k != k) { snprintf(c->err, sizeof c->err, "k=%d, expected %d", k, c->k); return -1; }
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t rc = ho_revcomp(kmers[i], k);
+        ho_set_insert(&c->set[index], kmers[i] < rc ? kmers[i] : rc);
+    }
+    return (long)n;
+}
+
 static char *ho_slurp(const char *path, size_t *n) {
     FILE *f = fopen(path, "rb");
     if (!f) return NULL;

@@ -60,6 +60,8 @@ const char    *ho_error(const ho_classifier *c);
  * ("total_kmer"), or -1 on a line whose length != k (reference: assert). */
 long   ho_load_kmers_mem(ho_classifier *c, const char *text, size_t n, int index);
 long   ho_load_kmers_file(ho_classifier *c, const char *path, int index);
+/* harness convenience: packed words (kmer.h code) instead of text; canonicalised and inserted like load_kmers */
+long   ho_load_kmers_packed(ho_classifier *c, const uint64_t *kmers, size_t n, int k, int index);
 /* classify.cpp:314-339 erase the adaptors' canonical k-mers from both sets;
  * returns the number of erased set members, -1 if an adaptor is shorter than k */
 long   ho_init_adaptor(ho_classifier *c, const char *fwd, const char *rev);

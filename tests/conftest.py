@@ -47,7 +47,7 @@ def _built():
 @pytest.fixture(scope="session", params=[3, 1, 0, 2, 4], ids=["prefilter_mini", "prefilter", "direct", "prefilter_tma", "prefilter_mini_tma"])
 def engine(request):
     """One context per fused-kernel variant: 3 = Bloom pre-filter addressed by the k-mer's minimizer + exact table (default;
-    k = 17/21/25/31, any other k runs as 1), 1 = pre-filter addressed by a hash of the k-mer, 2 = the same with TMA-staged read
+    k = 21/25/31; any other k, 17 included, runs as 1), 1 = pre-filter addressed by a hash of the k-mer, 2 = the same with TMA-staged read
     bytes, 4 = 3 with TMA-staged read bytes, 0 = direct table probe per position.  All must be bit-identical to the oracle."""
     from hast_b200.capi import Engine
     e = Engine(0)

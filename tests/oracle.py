@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
         l.ho_load_kmers_mem.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_int]
         l.ho_load_kmers_file.restype = i64
         l.ho_load_kmers_file.argtypes = [vp, C.c_char_p, C.c_int]
+        l.ho_load_kmers_packed.restype = i64
+        l.ho_load_kmers_packed.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int]
         l.ho_init_adaptor.restype = i64
         l.ho_init_adaptor.argtypes = [vp, C.c_char_p, C.c_char_p]
         l.ho_k.argtypes = [vp]
@@ -93,6 +95,10 @@ class Oracle:
 
     def load_kmers_file(self, path, index: int) -> int:
         return self.l.ho_load_kmers_file(self.c, str(path).encode(), index)
+
+    def load_kmers_packed(self, kmers: np.ndarray, k: int, index: int) -> int:
+        km = np.ascontiguousarray(kmers, np.uint64)
+        return self.l.ho_load_kmers_packed(self.c, km.ctypes.data, km.size, k, index)
 
     def init_adaptor(self, fwd: bytes = ADAPTOR_F, rev: bytes = ADAPTOR_R) -> int:
         return self.l.ho_init_adaptor(self.c, fwd, rev)

@@ -164,3 +164,21 @@ def test_oracle_matches_live_reference(k, seed, tmp_path):
             assert (int(table[nm][2]), int(table[nm][3])) == tuple(counts[i]), nm
         else:
             assert not (c["bc_ids"] == i).any()
+
+
+def test_packed_loader_equals_text_loader():
+    """ho_load_kmers_packed (harness convenience for the large configurations) builds the same sets as load_kmers."""
+    from hast_b200 import synth
+    t = synth.make_trio(synth.config("tiny"))
+    a, b = orc.Oracle(), orc.Oracle()
+    for i in (0, 1):
+        a.load_kmers(t.kmer_text(i), i)
+        km = t.pat if i == 0 else t.mat
+        flip = np.arange(km.size) % 3 == 0                      # any orientation is canonicalised on load
+        b.load_kmers_packed(np.where(flip, synth.revcomp_packed(km, t.spec.k), km), t.spec.k, i)
+    a.init_adaptor(); b.init_adaptor()
+    assert (a.set_size(0), a.set_size(1)) == (b.set_size(0), b.set_size(1))
+    bases, off, bc = t.batch()
+    ca, la = a.classify_batch(bases, off.astype(np.uint64), bc, t.n_barcodes)
+    cb, lb = b.classify_batch(bases, off.astype(np.uint64), bc, t.n_barcodes)
+    assert la == lb and (ca == cb).all() and ca.sum() > 0
