@@ -10,8 +10,10 @@
 // chunks that never move, and a table that fills up is replaced by a larger
 // copy while the old one stays alive for the readers still probing it (they
 // can only miss, and a miss re-probes the current table under the shard lock).
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <new>
 #include <mutex>
 #include <sys/mman.h>
 #include <thread>
@@ -21,18 +23,25 @@
 namespace hasthost {
 
 namespace {
+inline uint64_t load64(const char* s) { uint64_t w; memcpy(&w, s, 8); return w; }
+inline uint64_t load32(const char* s) { uint32_t w; memcpy(&w, s, 4); return w; }
 inline uint64_t hash_bytes(const char* s, size_t n) {
-    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdull);
-    while (n >= 8) {
-        uint64_t w;
-        memcpy(&w, s, 8);
-        h = (h ^ w) * 0xff51afd7ed558ccdull;
-        h ^= h >> 32;
-        s += 8; n -= 8;
+    // Names of 1..16 bytes (every stLFR barcode, "1234_567_89") take two possibly overlapping fixed-size loads
+    // and no loop; the length is mixed in, so a name and its prefix differ.
+    uint64_t a, b;
+    if (n >= 8 && n <= 16) { a = load64(s); b = load64(s + n - 8); }
+    else if (n >= 4 && n < 8) { a = load32(s); b = load32(s + n - 4); }
+    else if (n < 4) { a = n ? ((uint64_t)(uint8_t)s[0] | (uint64_t)(uint8_t)s[n >> 1] << 8 | (uint64_t)(uint8_t)s[n - 1] << 16) : 0; b = 0; }
+    else {
+        uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdull);
+        size_t m = n;
+        const char* p = s;
+        while (m > 16) { h = (h ^ load64(p)) * 0xff51afd7ed558ccdull; h ^= h >> 32; p += 8; m -= 8; }
+        a = load64(p) ^ h; b = load64(p + m - 8);
     }
-    uint64_t w = 0;
-    memcpy(&w, s, n);
-    h = (h ^ w) * 0xc4ceb9fe1a85ec53ull;
+    uint64_t h = (a ^ 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdull)) * 0xff51afd7ed558ccdull;
+    h ^= h >> 32;
+    h = (h ^ b) * 0xc4ceb9fe1a85ec53ull;
     h ^= h >> 29;
     h *= 0xff51afd7ed558ccdull;
     h ^= h >> 32;
@@ -84,20 +93,30 @@ private:
 struct Table {
     Table(size_t n, HugeArena& arena) : mask(n - 1) {
         slots = static_cast<Entry*>(arena.alloc(n * sizeof(Entry)));
-        if (!slots) {
-            owned.reset(new Entry[n]);
-            slots = owned.get();
+        if (!slots) {                                    // only when the arena could not serve
+            owned = aligned_alloc(64, n * sizeof(Entry));
+            if (!owned) throw std::bad_alloc();
+            memset(owned, 0, n * sizeof(Entry));
+            slots = static_cast<Entry*>(owned);
         }
     }
+    ~Table() { free(owned); }
+    Table(const Table&) = delete;
+    // what readers load: the slot array (64-byte aligned) with log2 of its size in the low bits, so that a
+    // lookup is two dependent loads (this word, then the slot) instead of three
+    uintptr_t tagged() const { return reinterpret_cast<uintptr_t>(slots) | (uintptr_t)__builtin_ctzll(mask + 1); }
     size_t mask;
     Entry* slots;
-    std::unique_ptr<Entry[]> owned;                      // only when the arena could not serve
+    void* owned = nullptr;
 };
+inline const Entry* tagged_slots(uintptr_t t) { return reinterpret_cast<const Entry*>(t & ~(uintptr_t)63); }
+inline size_t tagged_mask(uintptr_t t) { return ((size_t)1 << (t & 63)) - 1; }
 constexpr size_t kArenaChunk = 1u << 16;
 }  // namespace
 
 struct BarcodeIndex::Shard {
     std::atomic<Table*> cur{nullptr};
+    std::atomic<uintptr_t>* pub = nullptr;               // this shard's word in BarcodeIndex::Arena::pub
     std::mutex mu;
     std::vector<std::unique_ptr<Table>> tables;          // every generation stays alive
     std::vector<std::unique_ptr<char[]>> chunks;         // strings never move
@@ -106,10 +125,12 @@ struct BarcodeIndex::Shard {
     char pad[64];
 
     HugeArena* arena = nullptr;
-    void init(HugeArena* a) {
+    void init(HugeArena* a, std::atomic<uintptr_t>* p) {
         arena = a;
+        pub = p;
         tables.emplace_back(new Table(1024, *arena));
         cur.store(tables.back().get(), std::memory_order_release);
+        pub->store(tables.back()->tagged(), std::memory_order_release);
     }
     const char* store(const char* s, size_t n) {
         if (n > kArenaChunk / 4) {                       // an oversized name gets a chunk of its own
@@ -141,37 +162,42 @@ struct BarcodeIndex::Shard {
         }
         tables.push_back(std::move(nt));
         cur.store(tables.back().get(), std::memory_order_release);
+        pub->store(tables.back()->tagged(), std::memory_order_release);
     }
 };
 
-struct BarcodeIndex::Arena : HugeArena {};
+struct BarcodeIndex::Arena : HugeArena {
+    alignas(64) std::atomic<uintptr_t> pub[BarcodeIndex::kShards];   // current table of every shard, 2 KiB: cache resident
+};
 BarcodeIndex::BarcodeIndex() : arena_(new Arena()), shards_(new Shard[kShards]) {
-    for (int s = 0; s < kShards; ++s) shards_[s].init(arena_.get());
+    for (int s = 0; s < kShards; ++s) shards_[s].init(arena_.get(), &arena_->pub[s]);
 }
 BarcodeIndex::~BarcodeIndex() = default;
 
 uint64_t BarcodeIndex::hash(const char* s, size_t n) { return hash_bytes(s, n); }
 
 void BarcodeIndex::prefetch(uint64_t h) const {
-    const Table* t = shards_[h & (kShards - 1)].cur.load(std::memory_order_acquire);
-    __builtin_prefetch(&t->slots[(size_t)(h >> 8) & t->mask]);
+    const uintptr_t t = arena_->pub[h & (kShards - 1)].load(std::memory_order_acquire);
+    __builtin_prefetch(&tagged_slots(t)[(size_t)(h >> 8) & tagged_mask(t)]);
 }
 
 uint32_t BarcodeIndex::intern(const char* s, size_t n) { return intern_hashed(hash_bytes(s, n), s, n); }
 
 uint32_t BarcodeIndex::intern_hashed(uint64_t h, const char* s, size_t n) {
-    Shard& sh = shards_[h & (kShards - 1)];
     {                                                    // lock-free: seen before
-        const Table* t = sh.cur.load(std::memory_order_acquire);
-        size_t i = (size_t)(h >> 8) & t->mask;
+        const uintptr_t t = arena_->pub[h & (kShards - 1)].load(std::memory_order_acquire);
+        const Entry* const slots = tagged_slots(t);
+        const size_t mask = tagged_mask(t);
+        size_t i = (size_t)(h >> 8) & mask;
         for (;;) {
-            const Entry& e = t->slots[i];
+            const Entry& e = slots[i];
             const uint64_t eh = e.hash.load(std::memory_order_acquire);
             if (!eh) break;
             if (eh == h && e.len == n && memcmp(e.data(), s, n) == 0) return e.id;
-            i = (i + 1) & t->mask;
+            i = (i + 1) & mask;
         }
     }
+    Shard& sh = shards_[h & (kShards - 1)];
     std::lock_guard<std::mutex> lk(sh.mu);
     Table* t = sh.cur.load(std::memory_order_relaxed);
     size_t i = (size_t)(h >> 8) & t->mask;

@@ -113,6 +113,7 @@ bool FastqSource::next(TextBlock& blk, size_t target, std::string& err) {
     carry_.clear();
     carry_lines_ = 0;
     blk.last_of_file = false;
+    blk.begin = 0;
     for (;;) {
         while (!eof_ && len < target) {
             const size_t n = raw_read(blk.data.data() + len, cap - len, err);

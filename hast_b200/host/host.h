@@ -76,10 +76,21 @@ private:
 // A block holds whole records only (the reader cuts at a newline where the line
 // count is a multiple of four, classify.cpp:257-269 framing).
 struct TextBlock {
-    std::vector<char> data;
+    std::vector<char> data;      // owned storage (stream readers); unused when view is set
+    const char* view = nullptr;  // records live in a file mapping: view[0, len)
+    size_t begin = 0;            // owned storage: the records are data[begin, begin + len)
     size_t len = 0;
     bool last_of_file = false;   // the final block may end in a partial record / unterminated line
+    // optional: offsets of every '\n' of the block (relative to its start), made by the producer in the pass
+    // that framed the block -- nl[nl_begin, nl_begin + nl_count)
+    std::vector<uint32_t> nl;
+    size_t nl_begin = 0, nl_count = 0;
+    bool has_nl = false;
+    const char* text() const { return view ? view : data.data() + begin; }
 };
+// Offsets of every '\n' in p[0, n), appended to out from index `at` on (out is grown as needed); returns the
+// number found.  One AVX2 pass.
+size_t newline_index(const char* p, size_t n, std::vector<uint32_t>& out, size_t at);
 
 // One parsed batch in pinned memory, laid out for hast_submit_batch.
 struct Batch {
@@ -111,7 +122,10 @@ inline void parse_name(const char* head, size_t len, size_t& start, size_t& blen
 
 // Parse one block into a batch.  Returns false on a framing error that the
 // reference would have died on (message in batch.error).
-bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out);
+// resume (optional, in/out): offset inside the block where parsing starts; on return the offset where it
+// stopped -- blk.len unless the batch filled up first (very short records), in which case the caller
+// submits this batch and calls again with a fresh one.
+bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out, size_t* resume = nullptr);
 // Append `n` ASCII bases to a 2-bit MSB-first stream (kmer.h:11 code, kmer.h:156-160 order).
 // `acc`/`nbits` carry the partially filled word between calls; returns true if an 'N' was seen.
 bool pack_append(const char* seq, size_t n, uint32_t* words, size_t& n_words, uint64_t& acc, unsigned& nbits);

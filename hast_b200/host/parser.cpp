@@ -71,51 +71,61 @@ bool pack_append(const char* seq, size_t n, uint32_t* words, size_t& n_words, ui
 
 // Offsets of every '\n' of a block, found in one vector pass (the record loop below then walks this index
 // instead of calling memchr four times per record).
-__attribute__((target("avx2"))) static void newline_index_avx2(const char* p, size_t n, std::vector<uint32_t>& nl) {
+__attribute__((target("avx2"))) static size_t newline_index_avx2(const char* p, size_t n, std::vector<uint32_t>& nl, size_t at) {
     const __m256i c = _mm256_set1_epi8('\n');
-    size_t i = 0;
+    size_t i = 0, k = at;
+    uint32_t* out = nl.data();
+    size_t cap = nl.size();
     for (; i + 32 <= n; i += 32) {
         const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + i));
         uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, c));
-        while (m) {
-            nl.push_back((uint32_t)i + (uint32_t)__builtin_ctz(m));
+        if (!m) continue;
+        if (k + 32 > cap) { nl.resize(std::max<size_t>(cap * 2, k + 4096)); out = nl.data(); cap = nl.size(); }
+        do {
+            out[k++] = (uint32_t)i + (uint32_t)__builtin_ctz(m);
             m &= m - 1;
-        }
+        } while (m);
     }
+    if (k + 32 > cap) { nl.resize(k + 64); out = nl.data(); }
     for (; i < n; ++i)
-        if (p[i] == '\n') nl.push_back((uint32_t)i);
+        if (p[i] == '\n') out[k++] = (uint32_t)i;
+    return k - at;
 }
-static void newline_index(const char* p, size_t n, std::vector<uint32_t>& nl) {
-    nl.clear();
+size_t newline_index(const char* p, size_t n, std::vector<uint32_t>& nl, size_t at) {
+    if (nl.size() < at + n / 48 + 64) nl.resize(at + n / 48 + 64);
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
-    if (have_avx2) return newline_index_avx2(p, n, nl);
-    const __m128i c = _mm_set1_epi8('\n');
-    size_t i = 0;
-    for (; i + 16 <= n; i += 16) {
-        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p + i));
-        uint32_t m = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, c));
-        while (m) {
-            nl.push_back((uint32_t)i + (uint32_t)__builtin_ctz(m));
-            m &= m - 1;
+    if (have_avx2) return newline_index_avx2(p, n, nl, at);
+    size_t k = at;
+    for (size_t i = 0; i < n; ++i)
+        if (p[i] == '\n') {
+            if (k >= nl.size()) nl.resize(nl.size() * 2);
+            nl[k++] = (uint32_t)i;
         }
-    }
-    for (; i < n; ++i)
-        if (p[i] == '\n') nl.push_back((uint32_t)i);
+    return k - at;
 }
 
-bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out) {
+bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out, size_t* resume) {
     const bool packed = out.packed != nullptr;
     size_t n_words = 0;
     uint64_t acc = 0;
     unsigned nbits = 0;
-    const char* const base = blk.data.data();
+    const size_t skip = resume ? *resume : 0;             // records before this offset went into earlier batches
+    const char* const base = blk.text() + skip;
     const char* p = base;
-    const char* const end = p + blk.len;
-    if (blk.len > 0xFFFFFFFFull) { out.error = "FASTQ block larger than 4 GiB"; return false; }
+    const size_t len = blk.len - skip;
+    const char* const end = p + len;
+    if (resume) *resume = blk.len;
+    if (len > 0xFFFFFFFFull) { out.error = "FASTQ block larger than 4 GiB"; return false; }
     static thread_local std::vector<uint32_t> nl_index;   // one per parser thread, reused from block to block
-    newline_index(base, blk.len, nl_index);
-    const uint32_t* const nls = nl_index.data();
-    const size_t n_nl = nl_index.size();
+    const uint32_t* nls;
+    size_t n_nl;
+    if (blk.has_nl && skip == 0) {                        // the producer indexed the block while framing it
+        nls = blk.nl.data() + blk.nl_begin;
+        n_nl = blk.nl_count;
+    } else {
+        n_nl = newline_index(base, len, nl_index, 0);
+        nls = nl_index.data();
+    }
     size_t li = 0;                                        // next unused entry of nls: the newline that ends line li
     out.n_reads = 0;
     out.n_bases = 0;
@@ -143,8 +153,11 @@ bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out) {
         if (li + 1 < n_nl) { nl = base + nls[li + 1]; slen = (size_t)(nl - p); p = nl + 1; }
         else { slen = (size_t)(end - p); p = end; }
         if (n >= out.cap_reads || nb + slen > (packed ? out.cap_words * 16 - 16 : out.cap_bases)) {
-            out.error = "FASTQ records too small for the batch buffers (raise HAST_BLOCK_MB?)";
-            return false;
+            // the batch is full before the block is used up (records far shorter than the sizing assumes):
+            // hand this batch over and let the caller come back for the rest of the block
+            if (n == 0 || !resume) { out.error = "FASTQ record larger than the batch buffers (raise HAST_BLOCK_MB)"; return false; }
+            *resume = skip + (size_t)(head - base);
+            break;
         }
         size_t bs, bl;
         parse_name(head, hlen, bs, bl);                   // classify.cpp:112-119

@@ -1,7 +1,9 @@
 // pipeline.cpp -- the streaming host pipeline of bin/classify.
 //
-//   reader thread   : every --read file in turn, read()/gzread() into text blocks of
-//                     whole records                       (processFastq, classify.cpp:238-269)
+//   plain files     : every parser thread claims slices of the file, pread()s and frames them itself
+//                     (plain_slicer.h: exact four-line framing by newline count, any number of threads per file)
+//   gzip / pipes    : reader threads inflate (inflate_par.h) into text blocks of whole records
+//                                                         (processFastq, classify.cpp:238-269)
 //   parser threads  : block -> pinned batch; barcodes interned to dense ids
 //                     (parseName :112-119; MultiThread::submit's Buffer :121-127,211-219)
 //   one thread/GPU  : hast_submit_batch (async H2D + fused kernel), batches taken from a
@@ -16,12 +18,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <unistd.h>
 
 #include "../../include/hast_b200.h"
 #include "fastq_source.h"
 #include "host.h"
+#include "plain_slicer.h"
 
 namespace hasthost {
 
@@ -237,26 +241,43 @@ int run_classify(const Options& opt, RunStats& st) {
     }
     auto abort_all = [&] { q_text.abort(); q_text_free.abort(); q_batch.abort(); q_batch_free.abort(); };
 
-    // Readers: one thread per input file, several files at once.  Inflating a gzip stream is serial
-    // and by far the slowest stage of the whole program (~0.2-0.4 GB/s of text per core against
-    // > 100 GB/s the GPUs classify), but the files of a run (r1/r2, lanes) are independent and the
-    // per-barcode sums do not depend on the order in which reads arrive.
+    // Plain regular files are read by the parser threads themselves, slice by slice (plain_slicer.h).  Everything
+    // else -- gzip, pipes, standard input -- is a serial stream and gets a reader thread per file, several files
+    // at once: inflating is the slowest stage of the whole program (~0.3-0.7 GB/s of text per core against
+    // > 100 GB/s the GPUs classify), but the files of a run (r1/r2, lanes) are independent and the per-barcode sums
+    // do not depend on the order in which reads arrive.
     std::atomic<uint64_t> text_bytes{0};
+    std::vector<std::unique_ptr<PlainSlicer>> plain;
+    std::vector<std::string> streams;
+    for (const std::string& path : opt.reads) {
+        const size_t n = path.size();
+        const bool gz = n > 3 && path.compare(n - 3, 3, ".gz") == 0;      // classify.cpp:245-250
+        if (!gz && path != "-" && !getenv("HAST_SERIAL_READER")) {
+            std::unique_ptr<PlainSlicer> sl(new PlainSlicer());
+            size_t slice_bytes = block_bytes - 8192;
+            if (const char* sb = getenv("HAST_SLICE_BYTES")) slice_bytes = (size_t)std::max(1L, atol(sb));   // tests: slices of a few bytes
+            const std::string e = sl->open(path, slice_bytes);
+            if (!e.empty()) { fprintf(stderr, "ERROR : %s\n", e.c_str()); free_batches(); cleanup(); return 1; }
+            if (sl->usable()) { plain.push_back(std::move(sl)); continue; }
+        }
+        streams.push_back(path);
+    }
     std::atomic<size_t> next_file{0};
-    const int n_readers = (int)std::max<size_t>(1, std::min<size_t>({opt.reads.size(), (size_t)opt.threads, (size_t)8}));
+    const int n_readers = (int)std::min<size_t>({streams.size(), (size_t)opt.threads, (size_t)8});
     // threads per gzip stream (inflate_par.h)
     // decoding one gzip stream on several threads costs ~2.5x the parser's CPU per byte: three
     // quarters of the cores go to the decoders, shared by the files read side by side
-    int inflate_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() * 3u / 4u / (unsigned)n_readers));
+    int inflate_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() * 3u / 4u / (unsigned)std::max(1, n_readers)));
     if (const char* e = getenv("HAST_INFLATE_THREADS")) inflate_threads = std::max(1, atoi(e));
     std::atomic<int> readers_left{n_readers};
     std::vector<std::thread> readers;
+    if (n_readers == 0) q_text.finish();
     for (int r = 0; r < n_readers; ++r)
         readers.emplace_back([&] {
             for (;;) {
                 const size_t fi = next_file.fetch_add(1);
-                if (fi >= opt.reads.size() || sh.failed) break;
-                const std::string& path = opt.reads[fi];
+                if (fi >= streams.size() || sh.failed) break;
+                const std::string& path = streams[fi];
                 fprintf(stderr, "__process read: %s\n", path.c_str());
                 FastqSource src;
                 std::string e = src.open(path, inflate_threads);
@@ -278,22 +299,48 @@ int run_classify(const Options& opt, RunStats& st) {
         });
 
     std::atomic<int> parsers_left{opt.threads};
+    std::atomic<size_t> plain_cursor{0};
     std::vector<std::thread> parsers;
     for (int t = 0; t < opt.threads; ++t)
         parsers.emplace_back([&] {
-            TextBlock* blk = nullptr;
-            while (q_text.pop(blk)) {
-                Batch* b = nullptr;
-                if (!q_batch_free.pop(b)) break;
-                if (blk->len + 4096 > b->cap_bases) {          // an oversized block (very long records)
-                    sh.fail("FASTQ record larger than the batch buffer; raise HAST_BLOCK_MB");
-                    abort_all();
-                    break;
+            // block -> one batch (several when the records are far shorter than the buffers were sized for)
+            auto parse_and_push = [&](const TextBlock& blk) -> bool {
+                size_t pos = 0;
+                while (pos < blk.len) {
+                    Batch* b = nullptr;
+                    if (!q_batch_free.pop(b)) return false;
+                    if (blk.len - pos + 4096 > b->cap_bases) {     // an oversized block (very long records)
+                        sh.fail("FASTQ record larger than the batch buffer; raise HAST_BLOCK_MB");
+                        abort_all();
+                        return false;
+                    }
+                    if (!parse_block(blk, index, *b, &pos)) { sh.fail(b->error); abort_all(); return false; }
+                    if (!q_batch.push(b)) return false;
                 }
-                const bool ok = parse_block(*blk, index, *b);
+                return true;
+            };
+            bool alive = true;
+            TextBlock own;                                        // plain files: this thread's slice buffer
+            while (alive) {
+                const size_t fi = plain_cursor.load(std::memory_order_acquire);
+                if (fi >= plain.size() || sh.failed) break;
+                bool first = false;
+                if (!plain[fi]->next(own, &first)) {          // file used up: move everybody on to the next one
+                    if (first) fprintf(stderr, "__process read: %s\n", plain[fi]->path().c_str());   // an empty file
+                    size_t expect = fi;
+                    plain_cursor.compare_exchange_strong(expect, fi + 1);
+                    continue;
+                }
+                if (first) {
+                    fprintf(stderr, "__process read: %s\n", plain[fi]->path().c_str());
+                    text_bytes += plain[fi]->size();
+                }
+                if (own.len) alive = parse_and_push(own);
+            }
+            TextBlock* blk = nullptr;
+            while (alive && q_text.pop(blk)) {
+                alive = parse_and_push(*blk);
                 q_text_free.push(blk);
-                if (!ok) { sh.fail(b->error); abort_all(); break; }
-                if (!q_batch.push(b)) break;
             }
             if (--parsers_left == 0) q_batch.finish();
         });

@@ -37,10 +37,14 @@ def test_usage_and_exit_255(args):
         assert run([ref] + args).returncode == 255
 
 
-def parse_only(files, threads=3, block_mb=None):
+def parse_only(files, threads=3, block_mb=None, slice_bytes=None, serial=False):
     env = dict(os.environ, HAST_PARSE_ONLY="1")
     if block_mb is not None:
         env["HAST_BLOCK_MB"] = str(block_mb)
+    if slice_bytes is not None:
+        env["HAST_SLICE_BYTES"] = str(slice_bytes)
+    if serial:
+        env["HAST_SERIAL_READER"] = "1"
     cmd = [CLASSIFY, "--hap0", "x", "--hap1", "y", "-t", str(threads)]
     for f in files:
         cmd += ["--read", f]
@@ -90,6 +94,45 @@ def test_front_end_eof_semantics(tmp_path):
     r = run([CLASSIFY, "--hap0", "x", "--hap1", "y", "--read", tmp_path / "missing.fq"],
             env=dict(os.environ, HAST_PARSE_ONLY="1"))
     assert r.returncode == 1 and b"cannot open" in r.stderr
+
+
+@pytest.mark.parametrize("slice_bytes", [1, 7, 64, 257, 4096, 100_000])
+def test_plain_files_sliced_across_threads_frame_like_getline(tmp_path, slice_bytes):
+    """plain_slicer.h: many threads per plain file, records framed by newline COUNT (classify.cpp:257-269 validates
+    neither '@' nor '+').  Quality lines that start with '@' or '+', '@' lines in sequence position, empty lines,
+    records longer than a slice, CRLF, an unterminated tail: every slice size gives the serial reader's answer."""
+    rng = np.random.default_rng(slice_bytes)
+    heads, reads, quals = [], [], []
+    for i in range(1500):
+        bc = b"%d_%d_%d" % tuple(rng.integers(1, 40, 3))
+        heads.append(b"@r%d#%s/%d" % (i, bc, 1 + i % 2) if i % 11 else b"@no barcode here %d" % i)
+        L = int(rng.integers(0, 300)) if i % 97 else 9000            # some records far longer than the small slices
+        reads.append(bytes(rng.choice(list(b"ACGTN@+"), L).astype(np.uint8)))
+        quals.append(bytes(rng.choice(list(b"@+F#/I\r"), L).astype(np.uint8)))
+    body = b"".join(h + b"\n" + r + b"\n+" + (h[1:] if i % 5 == 0 else b"") + b"\n" + q + b"\n"
+                    for i, (h, r, q) in enumerate(zip(heads, reads, quals)))
+    (tmp_path / "a.fq").write_bytes(body)
+    (tmp_path / "b.fq").write_bytes(body + b"@tail#9_9_9/1\nACGT")          # unterminated sequence line at EOF
+    (tmp_path / "c.fq").write_bytes(body + b"@tail#9_9_9/1")                  # unterminated header: dropped
+    want_a = expected_parse(heads, reads)
+    for f, extra in (("a.fq", ([], [])), ("b.fq", ([b"@tail#9_9_9/1"], [b"ACGT"])), ("c.fq", ([], []))):
+        want = expected_parse(heads + extra[0], reads + extra[1])
+        assert parse_only([tmp_path / f], serial=True) == want
+        for threads in (1, 5):
+            assert parse_only([tmp_path / f], threads=threads, slice_bytes=slice_bytes) == want
+    two = parse_only([tmp_path / "a.fq", tmp_path / "b.fq"], threads=4, slice_bytes=slice_bytes)
+    assert two == expected_parse(heads * 2 + [b"@tail#9_9_9/1"], reads * 2 + [b"ACGT"])
+    assert want_a == parse_only([tmp_path / "a.fq"], threads=3)             # default slice size
+
+
+def test_tiny_records_fill_a_batch_before_the_block_ends(tmp_path):
+    """Records far shorter than the batch buffers were sized for: the block is parsed into several batches."""
+    n = 700_000
+    body = b"".join(b"@#%d/1\nA\n+\nF\n" % (i % 7) for i in range(n))
+    (tmp_path / "t.fq").write_bytes(body)
+    want = b"".join(b"%d\t%d\t%d\n" % (j, len(range(j, n, 7)), len(range(j, n, 7))) for j in range(7))
+    assert parse_only([tmp_path / "t.fq"], threads=2) == want
+    assert parse_only([tmp_path / "t.fq"], threads=2, serial=True) == want
 
 
 def test_output_order_is_bytewise(tmp_path):
