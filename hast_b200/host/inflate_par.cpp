@@ -28,8 +28,11 @@ constexpr uint32_t kKindMask = 3u << 6;
 constexpr uint32_t kLit = 0u << 6, kBase = 1u << 6, kEob = 2u << 6, kSub = 3u << 6;
 constexpr int kLitlenRoot = GzipInflater::kLitlenRoot, kDistRoot = GzipInflater::kDistRoot;
 constexpr size_t kWindow = GzipInflater::kWindow;
-constexpr uint16_t kPlaceholder = 0x8000;
-constexpr size_t kMaxChunkOut = (size_t)1 << 29;            // symbols; a runaway decoder stops here
+constexpr size_t kMaxChunkOut = (size_t)1 << 31;            // bytes; a runaway decoder stops here
+constexpr size_t kSlack = 258 + 64;                         // wild copies may run past the end of a chunk's output
+// token: literal run, then (unless kNoMatch) one match
+constexpr uint32_t kNoMatch = 1u << 23;
+inline uint32_t make_token(uint32_t lits, uint32_t length, uint32_t dist) { return (lits << 24) | ((length - 3u) << 15) | (dist - 1u); }
 
 inline uint64_t load64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
@@ -80,7 +83,7 @@ struct Tables {
 };
 
 // Dynamic block header after BFINAL/BTYPE (RFC 1951 3.2.7), every rule enforced.
-bool parse_dynamic_header(BitReader& r, Tables& t) {
+bool parse_dynamic_header(BitReader& r, Tables& t, bool pack_literals = false) {
     const int hlit = (int)r.take(5) + 257, hdist = (int)r.take(5) + 1, hclen = (int)r.take(4) + 4;
     if (hlit > 286 || hdist > 30) return false;
     static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
@@ -129,7 +132,7 @@ bool parse_dynamic_header(BitReader& r, Tables& t) {
         if (r.overrun()) return false;
     }
     if (r.overrun() || lens[256] == 0) return false;
-    return GzipInflater::build_table(lens, hlit, kLitlenRoot, t.litlen, GzipInflater::kLitlenCap, true, false) &&
+    return GzipInflater::build_table(lens, hlit, kLitlenRoot, t.litlen, GzipInflater::kLitlenCap, true, pack_literals) &&
            GzipInflater::build_table(lens + hlit, hdist, kDistRoot, t.dist, GzipInflater::kDistCap, false, false);
 }
 
@@ -139,7 +142,7 @@ void build_fixed(Tables& t) {
     for (int i = 144; i < 256; ++i) lens[i] = 9;
     for (int i = 256; i < 280; ++i) lens[i] = 7;
     for (int i = 280; i < 288; ++i) lens[i] = 8;
-    GzipInflater::build_table(lens, 288, kLitlenRoot, t.litlen, GzipInflater::kLitlenCap, true, false);
+    GzipInflater::build_table(lens, 288, kLitlenRoot, t.litlen, GzipInflater::kLitlenCap, true, true);
     uint8_t d[32];
     for (int i = 0; i < 32; ++i) d[i] = 5;
     GzipInflater::build_table(d, 32, kDistRoot, t.dist, GzipInflater::kDistCap, false, false);
@@ -203,10 +206,14 @@ int64_t find_block_start(const uint8_t* in, size_t n, uint64_t from_bit, uint64_
 }
 
 struct Segment {
-    size_t begin, end;         // output range inside the chunk
+    size_t tok_begin, tok_end; // tokens of the segment
+    size_t lit_begin;          // its first literal byte
+    size_t out_len;            // bytes it decodes to
+    bool starts_member;        // a gzip header precedes it: the window starts empty
     bool member_end;           // ends with a gzip trailer
     uint32_t crc, isize;       // the trailer's values
-    uint32_t crc_got = 0;      // CRC-32 of the resolved bytes (phase 3b)
+    uint32_t crc_got = 0;      // CRC-32 of the replayed bytes
+    size_t out_begin = 0;      // offset of its bytes in the chunk's output (set by the replay)
 };
 
 }  // namespace
@@ -215,17 +222,66 @@ struct ParallelGzip::Chunk {
     uint64_t start_bit = 0;
     bool at_file_start = false;        // begins with the first gzip header of the file
     bool found = false;
-    std::unique_ptr<uint16_t[]> sym;   // [kWindow placeholders][output symbols]; kept across batches
-    size_t sym_cap = 0;
-    size_t n_out = 0;
+    std::vector<uint32_t> tok;         // buffers are kept across batches
+    std::vector<uint8_t> lit;
+    size_t n_tok = 0, n_lit = 0, n_out = 0;
     uint64_t end_bit = 0;
     std::vector<Segment> segs;
-    uint32_t max_reach = 0;            // deepest reference into the unknown window (first segment only)
     bool eof = false;
     int targets_passed = 0;
     std::string err;
-    std::vector<uint8_t> window;       // the 32 KiB that precede this chunk (phase 3a)
-    std::vector<uint8_t> bytes;        // resolved output (phase 3b)
+    ParallelGzip::Buffer bytes;        // [kWindow of history][n_out][kSlack]  (replay)
+};
+
+// One batch of chunks in flight: block starts are searched, then every chunk is decoded to tokens; the worker
+// that finishes the last search launches the decodes, the one that finishes the last decode wakes the coordinator.
+struct ParallelGzip::Batch {
+    std::vector<Chunk> chunks;
+    std::vector<size_t> order;         // chunks with a start, in stream order
+    uint64_t soft_stop = 0;
+    std::atomic<int> finds_left{0}, decodes_left{0};
+    bool ready = false;                // under pool mutex
+};
+
+// Worker pool of one stream: plain FIFO with a front door for the short CRC jobs.
+struct ParallelGzip::Pool {
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::deque<std::function<void()>> q;
+    std::vector<std::thread> th;
+    bool stop = false;
+    explicit Pool(int n) {
+        for (int i = 0; i < n; ++i)
+            th.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> f;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return stop || !q.empty(); });
+                        if (q.empty()) return;
+                        f = std::move(q.front());
+                        q.pop_front();
+                    }
+                    f();
+                }
+            });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+            q.clear();
+        }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+    void submit(std::function<void()> f, bool front = false) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (front) q.push_front(std::move(f)); else q.push_back(std::move(f));
+        }
+        cv.notify_one();
+    }
 };
 
 namespace {
@@ -252,40 +308,44 @@ bool parse_gzip_header(BitReader& r, std::string& err) {
     return true;
 }
 
-// Decode from c.start_bit until (a) a block boundary that is exactly the next still-reachable target, (b) once all
-// targets were run over, the first block boundary at or after soft_stop (0 = none), or (c) the end of the last member.
+// Entropy-decode from c.start_bit into tokens + literal bytes -- no output bytes are produced, so no window is
+// needed -- until (a) a block boundary that is exactly the next still-reachable target, (b) once all targets were
+// run over, the first block boundary at or after soft_stop (0 = none), or (c) the end of the last member.
 void decode_chunk(const uint8_t* in, size_t n, ParallelGzip::Chunk& c, const std::vector<uint64_t>& targets,
-                  uint64_t soft_stop) {
+                  uint64_t soft_stop, size_t chunk_bytes) {
     BitReader r(in, n);
     r.seek(c.start_bit);
     std::unique_ptr<Tables> dyn(new Tables), fixed;
-    if (c.sym_cap < kWindow + ((size_t)4 << 20)) {
-        c.sym_cap = kWindow + ((size_t)4 << 20);
-        c.sym.reset(new uint16_t[c.sym_cap]);
-    }
-    size_t cap = c.sym_cap;
-    for (size_t i = 0; i < kWindow; ++i) c.sym[i] = (uint16_t)(kPlaceholder | i);
-    uint16_t* buf = c.sym.get();
-    uint16_t* out = buf + kWindow;
+    if (c.tok.size() < chunk_bytes * 2) c.tok.resize(chunk_bytes * 2);
+    if (c.lit.size() < chunk_bytes * 6) c.lit.resize(chunk_bytes * 6);
+    uint32_t* tok = c.tok.data();
+    uint8_t* lit = c.lit.data();
+    size_t tok_cap = c.tok.size(), lit_cap = c.lit.size();
+    size_t nt = 0, nl = 0;
+    uint64_t match_sum = 0;                         // bytes produced by matches so far
+    uint32_t run = 0;                               // literals not yet attached to a token
     size_t ti = 0;
     bool in_member = !c.at_file_start;
-    bool window_reachable = !c.at_file_start;      // false once a member began inside this chunk
-    size_t member_base = 0;                         // output index where the current member began (if !window_reachable)
-    size_t seg_begin = 0;
     bool first_header = c.at_file_start;
+    bool seg_starts_member = false;
+    size_t seg_tok = 0, seg_lit = 0;
+    uint64_t seg_match = 0;
     auto fail = [&](const char* m) { c.err = m; };
-    auto grow = [&](size_t need) {
-        const size_t used = (size_t)(out - buf);
-        if (used + need <= cap) return true;
-        if (used - kWindow > kMaxChunkOut) { fail("chunk output too large for the parallel decoder (set HAST_INFLATE_THREADS=1)"); return false; }
-        cap = std::max(cap * 2, used + need);
-        std::unique_ptr<uint16_t[]> bigger(new uint16_t[cap]);
-        memcpy(bigger.get(), buf, used * sizeof(uint16_t));
-        c.sym = std::move(bigger);
-        c.sym_cap = cap;
-        buf = c.sym.get();
-        out = buf + used;
-        return true;
+    auto grow = [&](size_t need_tok, size_t need_lit) {
+        if (nt + need_tok > tok_cap) { c.tok.resize(std::max(tok_cap * 2, nt + need_tok)); tok = c.tok.data(); tok_cap = c.tok.size(); }
+        if (nl + need_lit > lit_cap) { c.lit.resize(std::max(lit_cap * 2, nl + need_lit)); lit = c.lit.data(); lit_cap = c.lit.size(); }
+    };
+    auto flush_run = [&] {
+        while (run) { const uint32_t k = std::min(run, 255u); tok[nt++] = (k << 24) | kNoMatch; run -= k; }
+    };
+    auto close_segment = [&](bool member_end, uint32_t crc, uint32_t isize) {
+        grow(8 + run / 255, 0);
+        flush_run();
+        const size_t out_len = (nl - seg_lit) + (size_t)(match_sum - seg_match);
+        if (nt > seg_tok || member_end || seg_starts_member)
+            c.segs.push_back(Segment{seg_tok, nt, seg_lit, out_len, seg_starts_member, member_end, crc, isize});
+        seg_tok = nt; seg_lit = nl; seg_match = match_sum;
+        seg_starts_member = false;
     };
 
     for (;;) {
@@ -297,8 +357,7 @@ void decode_chunk(const uint8_t* in, size_t n, ParallelGzip::Chunk& c, const std
             first_header = false;
             if (!parse_gzip_header(r, c.err)) break;
             in_member = true;
-            window_reachable = false;
-            member_base = (size_t)(out - buf) - kWindow;
+            seg_starts_member = true;
         }
         const uint64_t bp = r.bitpos();
         while (ti < targets.size() && bp > targets[ti]) { ++ti; ++c.targets_passed; }
@@ -319,9 +378,11 @@ void decode_chunk(const uint8_t* in, size_t n, ParallelGzip::Chunk& c, const std
             if ((len ^ 0xFFFFu) != nlen) { fail("invalid stored block lengths"); break; }
             size_t byte = (size_t)(r.bitpos() >> 3);
             if (byte + len > n) { fail("unexpected end of file"); break; }
-            if (!grow(len + 16)) break;
-            for (uint32_t i = 0; i < len; ++i) out[i] = in[byte + i];
-            out += len;
+            grow(len / 255 + 8 + run / 255, len + 16);
+            memcpy(lit + nl, in + byte, len);
+            nl += len;
+            run += len;
+            flush_run();
             r.seek((uint64_t)(byte + len) * 8);
         } else {
             const Tables* t;
@@ -329,36 +390,115 @@ void decode_chunk(const uint8_t* in, size_t n, ParallelGzip::Chunk& c, const std
                 if (!fixed) { fixed.reset(new Tables); build_fixed(*fixed); }
                 t = fixed.get();
             } else {
-                if (!parse_dynamic_header(r, *dyn)) { fail("invalid dynamic block header"); break; }
+                if (!parse_dynamic_header(r, *dyn, true)) { fail("invalid dynamic block header"); break; }
                 t = dyn.get();
             }
             const uint32_t* const lt = t->litlen;
             const uint32_t* const dt = t->dist;
-            uint16_t* cap_end = buf + cap - 272;
             bool ok = true;
-            for (;;) {
-                if (out > cap_end) {
-                    if (!grow(1u << 20)) { ok = false; break; }
-                    cap_end = buf + cap - 272;
-                }
-                if (r.pos >= n && r.overrun()) { fail("unexpected end of file"); ok = false; break; }
-                r.refill();
-                uint32_t e;
-                HASTP_LOOKUP(e, lt, kLitlenRoot, r);
-                if ((e & kKindMask) == kLit) {             // up to three literals out of one refill (56 bits)
-                    *out++ = (uint16_t)((e >> 8) & 0xFFu);
-                    r.drop(e & 15u);
-                    HASTP_LOOKUP(e, lt, kLitlenRoot, r);
-                    if ((e & kKindMask) == kLit) {
-                        *out++ = (uint16_t)((e >> 8) & 0xFFu);
-                        r.drop(e & 15u);
-                        HASTP_LOOKUP(e, lt, kLitlenRoot, r);
+            // the hot loop keeps the bit reader and the output cursors in locals (registers); inputs shorter than
+            // the 8-byte loads need are handled by the bounds-checked reader below
+            uint64_t bb = r.bb;
+            unsigned bc = r.bc;
+            size_t pos = r.pos;
+            const size_t fast_end = n >= 40 ? n - 40 : 0;      // an iteration refills at most three times (7 bytes each): every 8-byte load stays in bounds
+            constexpr uint32_t kRootMask = (1u << kLitlenRoot) - 1u, kDistMask = (1u << kDistRoot) - 1u;
+#define HT_REFILL()   do { bb |= load64(in + pos) << bc; pos += (63 - bc) >> 3; bc |= 56; } while (0)
+#define HT_DROP(k)    do { bb >>= (k); bc -= (k); } while (0)
+#define HT_SUB(e, table, root)                                                          \
+    do {                                                                                \
+        HT_DROP(root);                                                                  \
+        e = table[(e >> 16) + (bb & ((1u << ((e >> 8) & 31u)) - 1u))];                  \
+    } while (0)
+#define HT_LITERALS(e)                                    \
+    do {                                                  \
+        const uint32_t v_ = e >> 8;                       \
+        memcpy(lit + nl, &v_, 4);                         \
+        const uint32_t k_ = 1u + ((e >> 4) & 3u);         \
+        nl += k_;                                         \
+        run += k_;                                        \
+        HT_DROP(e & 15u);                                 \
+    } while (0)
+            uint32_t e;
+            bool eob = false;
+            if (pos < fast_end) {
+                HT_REFILL();
+                e = lt[bb & kRootMask];
+                for (;;) {
+                    if (nt + 8 > tok_cap || nl + 32 > lit_cap) grow(1u << 16, 1u << 18);
+                    if (pos >= fast_end) break;                // the careful loop below finishes the block
+                    if ((e & kKindMask) == kSub) HT_SUB(e, lt, kLitlenRoot);
+                    if ((e & kKindMask) == kLit) {             // up to nine literals out of one refill (56 bits)
+                        HT_LITERALS(e);
+                        e = lt[bb & kRootMask];
+                        if ((e & kKindMask) == kSub) HT_SUB(e, lt, kLitlenRoot);
                         if ((e & kKindMask) == kLit) {
-                            *out++ = (uint16_t)((e >> 8) & 0xFFu);
-                            r.drop(e & 15u);
-                            continue;
+                            HT_LITERALS(e);
+                            e = lt[bb & kRootMask];
+                            if ((e & kKindMask) == kSub) HT_SUB(e, lt, kLitlenRoot);
+                            if ((e & kKindMask) == kLit) {
+                                HT_LITERALS(e);
+                                HT_REFILL();
+                                e = lt[bb & kRootMask];
+                                continue;
+                            }
+                        }
+                        // e came out of the bits that are left: a length / distance pair needs up to 48 of them
+                        if (bc < 48) {
+                            // e's code bits are still at the bottom of bb, so a refill does not disturb it
+                            HT_REFILL();
                         }
                     }
+                    if ((e & kKindMask) == kEob) {
+                        if ((e >> 16) != 0) { fail("invalid literal/length code"); ok = false; }
+                        HT_DROP(e & 63u);
+                        eob = true;
+                        break;
+                    }
+                    const uint64_t saved = bb;
+                    const uint32_t cl = (e >> 8) & 31u, drop = e & 63u;
+                    HT_DROP(drop);
+                    const uint32_t length = (e >> 16) + (uint32_t)((saved >> cl) & ((1u << (drop - cl)) - 1u));
+                    uint32_t d = dt[bb & kDistMask];
+                    if ((d & kKindMask) == kSub) HT_SUB(d, dt, kDistRoot);
+                    if ((d & kKindMask) != kBase) { fail("invalid distance code"); ok = false; break; }
+                    const uint64_t saved2 = bb;
+                    const uint32_t cl2 = (d >> 8) & 31u, drop2 = d & 63u;
+                    HT_DROP(drop2);
+                    const uint32_t dist = (d >> 16) + (uint32_t)((saved2 >> cl2) & ((1u << (drop2 - cl2)) - 1u));
+                    HT_REFILL();
+                    e = lt[bb & kRootMask];                    // next symbol's entry: its load overlaps the bookkeeping
+                    if (run > 255) {
+                        if (nt + run / 255 + 8 > tok_cap) grow(run / 255 + (1u << 16), 0);
+                        while (run > 255) { tok[nt++] = (255u << 24) | kNoMatch; run -= 255; }
+                    }
+                    tok[nt++] = make_token(run, length, dist);
+                    run = 0;
+                    match_sum += length;
+                }
+            }
+            r.bb = bb; r.bc = bc; r.pos = pos;
+#undef HT_REFILL
+#undef HT_DROP
+#undef HT_SUB
+#undef HT_LITERALS
+#define HASTP_LITERALS(e)                                 \
+    do {                                                  \
+        const uint32_t v_ = e >> 8;                       \
+        memcpy(lit + nl, &v_, 4);                         \
+        const uint32_t k_ = 1u + ((e >> 4) & 3u);         \
+        nl += k_;                                         \
+        run += k_;                                        \
+        r.drop(e & 15u);                                  \
+    } while (0)
+            while (ok && !eob) {                               // last bytes of the input: bounds-checked reader
+                if (nt + 8 > tok_cap || nl + 32 > lit_cap) grow(1u << 16, 1u << 18);
+                if (r.pos >= n && r.overrun()) { fail("unexpected end of file"); ok = false; break; }
+                r.refill();
+                HASTP_LOOKUP(e, lt, kLitlenRoot, r);
+                if ((e & kKindMask) == kLit) {
+                    HASTP_LITERALS(e);
+                    continue;
                 }
                 if ((e & kKindMask) == kEob) {
                     if ((e >> 16) != 0) { fail("invalid literal/length code"); ok = false; }
@@ -369,7 +509,7 @@ void decode_chunk(const uint8_t* in, size_t n, ParallelGzip::Chunk& c, const std
                 const uint32_t cl = (e >> 8) & 31u, drop = e & 63u;
                 r.drop(drop);
                 const uint32_t length = (e >> 16) + (uint32_t)((saved >> cl) & ((1u << (drop - cl)) - 1u));
-                r.refill();                                // literals may have used the budget of the distance
+                r.refill();
                 uint32_t d;
                 HASTP_LOOKUP(d, dt, kDistRoot, r);
                 if ((d & kKindMask) != kBase) { fail("invalid distance code"); ok = false; break; }
@@ -377,74 +517,70 @@ void decode_chunk(const uint8_t* in, size_t n, ParallelGzip::Chunk& c, const std
                 const uint32_t cl2 = (d >> 8) & 31u, drop2 = d & 63u;
                 r.drop(drop2);
                 const uint32_t dist = (d >> 16) + (uint32_t)((saved2 >> cl2) & ((1u << (drop2 - cl2)) - 1u));
-                const size_t idx = (size_t)(out - buf) - kWindow;
-                if (window_reachable) {
-                    if (dist > idx && dist - idx > c.max_reach) c.max_reach = (uint32_t)(dist - idx);
-                } else if (dist > idx - member_base) {
-                    fail("invalid distance too far back");
-                    ok = false;
-                    break;
+                if (run > 255) {
+                    if (nt + run / 255 + 8 > tok_cap) grow(run / 255 + (1u << 16), 0);
+                    while (run > 255) { tok[nt++] = (255u << 24) | kNoMatch; run -= 255; }
                 }
-                const uint16_t* src = out - dist;
-                uint16_t* const end = out + length;
-                if (dist >= 8) {                           // most matches are short: 16 symbols unconditionally
-                    memcpy(out, src, 16);
-                    memcpy(out + 8, src + 8, 16);
-                    if (length > 16) {
-                        out += 16; src += 16;
-                        do { memcpy(out, src, 16); out += 8; src += 8; } while (out < end);
-                    }
-                } else if (dist >= 4) {
-                    do { memcpy(out, src, 8); out += 4; src += 4; } while (out < end);
-                } else {
-                    do { *out++ = *src++; } while (out < end);
-                }
-                out = end;
+                tok[nt++] = make_token(run, length, dist);
+                run = 0;
+                match_sum += length;
             }
+#undef HASTP_LITERALS
             if (!ok) break;
+            if (nl + match_sum > kMaxChunkOut) { fail("chunk output too large for the parallel decoder (set HAST_INFLATE_THREADS=1)"); break; }
         }
         if (last) {
             r.align();
             const uint32_t crc = r.take(32), isize = r.take(32);
             if (r.overrun()) { fail("unexpected end of file"); break; }
-            const size_t idx = (size_t)(out - buf) - kWindow;
-            c.segs.push_back(Segment{seg_begin, idx, true, crc, isize});
-            seg_begin = idx;
+            close_segment(true, crc, isize);
             in_member = false;
         }
     }
     c.end_bit = r.bitpos();
-    c.n_out = (size_t)(out - buf) - kWindow;
-    if (c.n_out > seg_begin) c.segs.push_back(Segment{seg_begin, c.n_out, false, 0, 0});
+    close_segment(false, 0, 0);
+    c.n_tok = nt;
+    c.n_lit = nl;
+    c.n_out = nl + (size_t)match_sum;
 }
 
-// 16-bit symbols -> bytes: literals are kept, placeholders read the window.  Sixteen at a time when none of them is
-// a placeholder; otherwise through a 64 Ki-entry table (identity below 0x8000, the window above), which has no branch
-// to mispredict -- in FASTQ the constant part of every read name is a placeholder all the way through a chunk.
-void resolve_symbols(const uint16_t* sym, size_t n, const uint8_t* lut, uint8_t* dst) {
-    size_t k = 0;
-    for (; k + 16 <= n; k += 16) {
-        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(sym + k));
-        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(sym + k + 8));
-        if (_mm_movemask_epi8(_mm_or_si128(a, b)) & 0xAAAA) {            // some value has bit 15 set
-            for (size_t j = k; j < k + 16; ++j) dst[j] = lut[sym[j]];
-        } else {
-            _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + k), _mm_packus_epi16(a, b));
+// Tokens -> bytes at `out`; the `avail` bytes in front of `out` are the member's history (at most the window counts).
+// Returns the end of the output or nullptr (a distance that reaches in front of the member).
+uint8_t* replay_tokens(const uint32_t* tok, size_t n_tok, const uint8_t* lit, uint8_t* out, uint64_t avail) {
+    const uint8_t* const begin = out;
+    for (size_t i = 0; i < n_tok; ++i) {
+        const uint32_t t = tok[i];
+        const uint32_t ll = t >> 24;
+        memcpy(out, lit, 16);                              // most literal runs are short
+        if (ll > 16) {
+            uint8_t* o = out + 16;
+            const uint8_t* s = lit + 16;
+            uint8_t* const e = out + ll;
+            do { memcpy(o, s, 16); o += 16; s += 16; } while (o < e);
         }
+        out += ll;
+        lit += ll;
+        if (t & kNoMatch) continue;
+        const uint32_t length = ((t >> 15) & 255u) + 3u, dist = (t & 0x7FFFu) + 1u;
+        if ((uint64_t)dist > avail + (uint64_t)(out - begin)) return nullptr;
+        const uint8_t* src = out - dist;
+        uint8_t* const end = out + length;
+        if (dist >= 16) {
+            memcpy(out, src, 16);
+            if (length > 16) {
+                out += 16; src += 16;
+                do { memcpy(out, src, 16); out += 16; src += 16; } while (out < end);
+            }
+        } else if (dist >= 8) {
+            do { memcpy(out, src, 8); out += 8; src += 8; } while (out < end);
+        } else if (dist == 1) {
+            memset(out, src[0], length);
+        } else {
+            do { *out++ = *src++; } while (out < end);
+        }
+        out = end;
     }
-    for (; k < n; ++k) dst[k] = lut[sym[k]];
-}
-
-template <class F>
-void parallel_for(int threads, size_t n, F&& f) {
-    if (n == 0) return;
-    std::atomic<size_t> next{0};
-    auto body = [&] { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); };
-    const int t = (int)std::min<size_t>((size_t)std::max(threads, 1), n);
-    std::vector<std::thread> pool;
-    for (int k = 1; k < t; ++k) pool.emplace_back(body);
-    body();
-    for (auto& th : pool) th.join();
+    return out;
 }
 
 }  // namespace
@@ -486,12 +622,58 @@ void ParallelGzip::open_memory(const uint8_t* data, size_t n) {
 
 void ParallelGzip::start() { coord_ = std::thread([this] { run(); }); }
 
-void ParallelGzip::push(std::vector<uint8_t>&& piece) {
-    if (piece.empty()) return;
+// Output buffers are recycled: a fresh 5 MB buffer costs more in page faults and zeroing than replaying into it.
+// Sizes are rounded up generously so that a recycled buffer nearly always fits the next chunk.
+ParallelGzip::Buffer ParallelGzip::take_buffer(size_t need) {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (size_t i = spare_.size(); i-- > 0;)
+            if (spare_[i].cap >= need) {
+                Buffer b = std::move(spare_[i]);
+                spare_.erase(spare_.begin() + (long)i);
+                return b;
+            }
+        if (spare_.size() >= 8) spare_.erase(spare_.begin());  // none fits: let the oldest small one go
+    }
+    if (getenv("HAST_PAR_PROF")) fprintf(stderr, "fresh buffer for %zu bytes\n", need);
+    return Buffer(std::max<size_t>(need + need / 2, (size_t)8 << 20));
+}
+
+void ParallelGzip::recycle(Buffer&& b) {
+    if (!b.cap) return;
+    std::lock_guard<std::mutex> lk(mu_);
+    if (spare_.size() < 64) spare_.push_back(std::move(b));
+}
+
+ParallelGzip::Buffer::Buffer(size_t n) {
+    const size_t huge = (size_t)2 << 20;
+    cap_map = (n + huge - 1) / huge * huge + huge;
+    void* m = mmap(nullptr, cap_map, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == MAP_FAILED) { cap_map = 0; return; }
+    map = m;
+    p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(m) + huge - 1) & ~(uintptr_t)(huge - 1));
+    cap = cap_map - (size_t)(p - static_cast<uint8_t*>(m));
+#ifdef MADV_HUGEPAGE
+    madvise(p, cap & ~(huge - 1), MADV_HUGEPAGE);
+#endif
+}
+ParallelGzip::Buffer::~Buffer() { if (map) munmap(map, cap_map); }
+ParallelGzip::Buffer::Buffer(Buffer&& o) noexcept : p(o.p), cap(o.cap), map(o.map), cap_map(o.cap_map) { o.p = nullptr; o.cap = 0; o.map = nullptr; o.cap_map = 0; }
+ParallelGzip::Buffer& ParallelGzip::Buffer::operator=(Buffer&& o) noexcept {
+    if (this != &o) {
+        if (map) munmap(map, cap_map);
+        p = o.p; cap = o.cap; map = o.map; cap_map = o.cap_map;
+        o.p = nullptr; o.cap = 0; o.map = nullptr; o.cap_map = 0;
+    }
+    return *this;
+}
+
+void ParallelGzip::push(Piece&& piece) {
+    if (!piece.len) { recycle(std::move(piece.buf)); return; }
     std::unique_lock<std::mutex> lk(mu_);
     cv_room_.wait(lk, [&] { return stop_ || ready_bytes_ < ((size_t)256 << 20); });
     if (stop_) return;
-    ready_bytes_ += piece.size();
+    ready_bytes_ += piece.len;
     ready_.push_back(std::move(piece));
     cv_out_.notify_one();
 }
@@ -516,154 +698,175 @@ bool ParallelGzip::next(const uint8_t** data, size_t* len) {
         err_ = err_pending_;
         return false;
     }
-    if (current_.capacity() && spare_.size() < 64) spare_.push_back(std::move(current_));
+    if (current_.buf.cap && spare_.size() < 64) spare_.push_back(std::move(current_.buf));
     current_ = std::move(ready_.front());
     ready_.pop_front();
-    ready_bytes_ -= current_.size();
+    ready_bytes_ -= current_.len;
     cv_room_.notify_one();
-    *data = current_.data();
-    *len = current_.size();
+    *data = current_.buf.p + current_.off;
+    *len = current_.len;
     return true;
 }
 
-void ParallelGzip::run() {
+// Launch one batch: search the block starts of chunks 1..W-1 (chunk 0 starts where the previous batch ended), then
+// decode every chunk that has a start up to the next one's.
+void ParallelGzip::launch(Batch& b, Pool& pool, uint64_t next_start, bool at_file_start) {
     const uint8_t* const in = in_;
     const size_t n = n_in_;
     const uint64_t n_bits = (uint64_t)n * 8;
-    uint64_t next_start = 0;
-    bool at_file_start = true;
-    std::vector<uint8_t> window(kWindow, 0);
+    const size_t W = b.chunks.size();
+    const size_t base = (size_t)(next_start >> 3);
+    for (Chunk& c : b.chunks) {                                // buffers stay, results go
+        c.found = false; c.at_file_start = false; c.n_out = c.n_tok = c.n_lit = 0; c.end_bit = 0; c.segs.clear();
+        c.eof = false; c.targets_passed = 0; c.err.clear();
+    }
+    b.chunks[0].start_bit = next_start;
+    b.chunks[0].at_file_start = at_file_start;
+    b.chunks[0].found = true;
+    const uint64_t batch_end = std::min<uint64_t>((uint64_t)(base + W * chunk_bytes_) * 8, n_bits);
+    b.soft_stop = batch_end < n_bits ? batch_end : 0;
+    b.order.clear();
+    {
+        std::lock_guard<std::mutex> lk(pool.mu);
+        b.ready = false;
+    }
+    auto launch_decodes = [this, &b, &pool, in, n] {
+        for (size_t k = 0; k < b.chunks.size(); ++k) if (b.chunks[k].found) b.order.push_back(k);
+        b.decodes_left.store((int)b.order.size());
+        for (size_t oi = 0; oi < b.order.size(); ++oi)
+            pool.submit([this, &b, &pool, in, n, oi] {
+                std::vector<uint64_t> targets;
+                for (size_t o = oi + 1; o < b.order.size(); ++o) targets.push_back(b.chunks[b.order[o]].start_bit);
+                decode_chunk(in, n, b.chunks[b.order[oi]], targets, b.soft_stop, chunk_bytes_);
+                if (b.decodes_left.fetch_sub(1) == 1) {
+                    { std::lock_guard<std::mutex> lk(pool.mu); b.ready = true; }
+                    pool.cv_done.notify_all();
+                }
+            });
+    };
+    if (W == 1) { launch_decodes(); return; }
+    b.finds_left.store((int)(W - 1));
+    for (size_t k = 1; k < W; ++k)
+        pool.submit([this, &b, in, n, n_bits, base, k, launch_decodes] {
+            const uint64_t from = (uint64_t)(base + k * chunk_bytes_) * 8, to = std::min<uint64_t>(from + (uint64_t)chunk_bytes_ * 8, n_bits);
+            if (from < n_bits) {
+                const int64_t s = find_block_start(in, n, from, to);
+                if (s >= 0) { b.chunks[k].start_bit = (uint64_t)s; b.chunks[k].found = true; }
+            }
+            if (b.finds_left.fetch_sub(1) == 1) launch_decodes();
+        });
+}
+
+void ParallelGzip::run() {
+    const size_t n = n_in_;
+    const uint64_t n_bits = (uint64_t)n * 8;
     uint32_t crc_run = (uint32_t)crc32(0L, Z_NULL, 0);
     uint64_t member_out = 0;
-    const size_t W = (size_t)std::max(2 * threads_, 2);
-    std::vector<Chunk> chunks(W);
+    // this thread replays; the others search and decode.  Two batches: one being decoded while the other is replayed.
+    const int n_workers = std::max(threads_ - 1, 1);
+    const size_t W = (size_t)std::max(2 * n_workers, 2);
+    Batch batches[2];
+    for (Batch& b : batches) b.chunks = std::vector<Chunk>(W);
+    std::vector<uint8_t> history(kWindow, 0);                  // last 32 KiB of output so far
     const bool prof = getenv("HAST_PAR_PROF") != nullptr;
-    double t_ph[5] = {0, 0, 0, 0, 0};
+    double t_ph[4] = {0, 0, 0, 0};
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    struct ProfOut { bool on; double* t; ~ProfOut() { if (on) fprintf(stderr, "phases: find %.3f decode %.3f window %.3f resolve %.3f emit %.3f s\n", t[0], t[1], t[2], t[3], t[4]); } } prof_out{prof, t_ph};
-
+    uint64_t n_tok_total = 0, n_lit_total = 0;
+    struct ProfOut { bool on; double* t; uint64_t* a; uint64_t* b2; ~ProfOut() { if (on) fprintf(stderr, "coordinator: wait-for-decode %.3f replay %.3f crc-wait %.3f emit %.3f s; %llu tokens, %llu literal bytes\n", t[0], t[1], t[2], t[3], (unsigned long long)*a, (unsigned long long)*b2); } } prof_out{prof, t_ph, &n_tok_total, &n_lit_total};
+    std::atomic<int> crc_left{0};
+    Pool pool(n_workers);                                      // declared last: joins its threads before the batches go
+    int cur = 0;
+    launch(batches[cur], pool, 0, true);
     for (;;) {
         {
             std::lock_guard<std::mutex> lk(mu_);
             if (stop_) return;
         }
-        const size_t base = (size_t)(next_start >> 3);
-        for (Chunk& c : chunks) {                           // buffers stay, results go
-            c.found = false; c.at_file_start = false; c.n_out = 0; c.end_bit = 0; c.segs.clear(); c.max_reach = 0;
-            c.eof = false; c.targets_passed = 0; c.err.clear();
-        }
-        chunks[0].start_bit = next_start;
-        chunks[0].at_file_start = at_file_start;
-        chunks[0].found = true;
-        const uint64_t batch_end = std::min<uint64_t>((uint64_t)(base + W * chunk_bytes_) * 8, n_bits);
-        const uint64_t soft_stop = batch_end < n_bits ? batch_end : 0;
+        Batch& b = batches[cur];
         double tp = now();
-        // phase 1: block starts
-        parallel_for(threads_, W - 1, [&](size_t j) {
-            const size_t k = j + 1;
-            const uint64_t from = (uint64_t)(base + k * chunk_bytes_) * 8, to = std::min<uint64_t>(from + (uint64_t)chunk_bytes_ * 8, n_bits);
-            if (from >= n_bits) return;
-            const int64_t s = find_block_start(in, n, from, to);
-            if (s >= 0) { chunks[k].start_bit = (uint64_t)s; chunks[k].found = true; }
-        });
+        {
+            std::unique_lock<std::mutex> lk(pool.mu);
+            pool.cv_done.wait(lk, [&] { return b.ready; });
+        }
         t_ph[0] += now() - tp; tp = now();
-        std::vector<size_t> order;                         // chunks with a start, in stream order
-        for (size_t k = 0; k < W; ++k) if (chunks[k].found) order.push_back(k);
         stats_.chunks += W;
-        stats_.starts_found += order.size() - 1;
+        stats_.starts_found += b.order.size() - 1;
         ++stats_.batches;
-        // phase 2: decode every chunk to the next start
-        parallel_for(threads_, order.size(), [&](size_t oi) {
-            std::vector<uint64_t> targets;
-            for (size_t o = oi + 1; o < order.size(); ++o) targets.push_back(chunks[order[o]].start_bit);
-            decode_chunk(in, n, chunks[order[oi]], targets, soft_stop);
-        });
-        t_ph[1] += now() - tp; tp = now();
-        // phase 3: the chain of chunks whose starts were confirmed by their predecessor
+        // the chain of chunks whose starts were confirmed by their predecessor
         std::vector<size_t> chain;
         bool eof = false;
-        for (size_t oi = 0; oi < order.size();) {
-            Chunk& c = chunks[order[oi]];
-            chain.push_back(order[oi]);
+        for (size_t oi = 0; oi < b.order.size();) {
+            Chunk& c = b.chunks[b.order[oi]];
+            chain.push_back(b.order[oi]);
             if (!c.err.empty()) { finish(c.err); return; }
             stats_.starts_dropped += (uint64_t)c.targets_passed;
             const size_t nxt = oi + 1 + (size_t)c.targets_passed;
             if (c.eof) { eof = true; break; }
-            if (nxt < order.size() && c.end_bit == chunks[order[nxt]].start_bit) { oi = nxt; continue; }
-            break;                                         // soft stop: the next batch starts exactly here
+            if (nxt < b.order.size() && c.end_bit == b.chunks[b.order[nxt]].start_bit) { oi = nxt; continue; }
+            break;                                             // soft stop: the next batch starts exactly here
         }
-        Chunk& last = chunks[chain.back()];
-        // 3a: windows, in stream order
+        const uint64_t next_start = b.chunks[chain.back()].end_bit;
+        if (!eof && next_start >= n_bits) { finish("unexpected end of file"); return; }   // ran out of input inside a member
+        if (!eof) launch(batches[cur ^ 1], pool, next_start, false);   // the workers move on while this thread replays
+        // replay, in stream order; the CRC of every finished chunk is computed by the workers (front of their queue)
         for (size_t ci : chain) {
-            Chunk& c = chunks[ci];
-            c.window = window;
-            const uint16_t* sym = c.sym.get() + kWindow;
-            if (c.n_out >= kWindow) {
-                for (size_t i = 0; i < kWindow; ++i) {
-                    const uint16_t v = sym[c.n_out - kWindow + i];
-                    window[i] = v < kPlaceholder ? (uint8_t)v : c.window[v - kPlaceholder];
-                }
-            } else {
-                std::vector<uint8_t> w(kWindow);
-                memcpy(w.data(), c.window.data() + c.n_out, kWindow - c.n_out);
-                for (size_t i = 0; i < c.n_out; ++i) {
-                    const uint16_t v = sym[i];
-                    w[kWindow - c.n_out + i] = v < kPlaceholder ? (uint8_t)v : c.window[v - kPlaceholder];
-                }
-                window.swap(w);
+            Chunk& c = b.chunks[ci];
+            const size_t need = kWindow + c.n_out + kSlack;
+            c.bytes = take_buffer(need);                       // recycled output buffers keep their pages
+            if (c.lit.size() < c.n_lit + 64) c.lit.resize(c.n_lit + 64);      // the literal copy reads 16 bytes at a time
+            if (!c.bytes.p) { finish("out of memory"); return; }
+            uint8_t* const base = c.bytes.p + kWindow;
+            n_tok_total += c.n_tok; n_lit_total += c.n_lit;
+            memcpy(c.bytes.p, history.data(), kWindow);
+            uint8_t* out = base;
+            for (Segment& sg : c.segs) {
+                if (sg.starts_member) member_out = 0;
+                sg.out_begin = (size_t)(out - base);
+                uint8_t* const end = replay_tokens(c.tok.data() + sg.tok_begin, sg.tok_end - sg.tok_begin, c.lit.data() + sg.lit_begin,
+                                                   out, std::min<uint64_t>(member_out, kWindow));
+                if (!end || (size_t)(end - out) != sg.out_len) { finish(end ? "internal: replay length mismatch" : "invalid distance too far back"); return; }
+                member_out += sg.out_len;
+                out = end;
+                if (sg.member_end) member_out = 0;
             }
+            if (c.n_out >= kWindow) memcpy(history.data(), base + c.n_out - kWindow, kWindow);
+            else if (c.n_out) {
+                memmove(history.data(), history.data() + c.n_out, kWindow - c.n_out);
+                memcpy(history.data() + kWindow - c.n_out, base, c.n_out);
+            }
+            crc_left.fetch_add(1);
+            pool.submit([&c, &crc_left, &pool, base] {
+                for (Segment& sg : c.segs) sg.crc_got = hast_crc32((uint32_t)crc32(0L, Z_NULL, 0), base + sg.out_begin, sg.out_len);
+                if (crc_left.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(pool.mu); pool.cv_done.notify_all(); }
+            }, true);
+        }
+        t_ph[1] += now() - tp; tp = now();
+        {
+            std::unique_lock<std::mutex> lk(pool.mu);
+            pool.cv_done.wait(lk, [&] { return crc_left.load() == 0; });
         }
         t_ph[2] += now() - tp; tp = now();
-        // 3b: bytes and per-segment CRC-32, in parallel
-        parallel_for(threads_, chain.size(), [&](size_t i) {
-            Chunk& c = chunks[chain[i]];
-            {
-                std::lock_guard<std::mutex> lk(mu_);       // recycled output buffers keep their pages
-                if (!spare_.empty()) { c.bytes = std::move(spare_.back()); spare_.pop_back(); }
-            }
-            if (c.bytes.capacity() < c.n_out) { std::vector<uint8_t>().swap(c.bytes); c.bytes.reserve(c.n_out + c.n_out / 8); }
-            c.bytes.resize(c.n_out);
-            const uint16_t* sym = c.sym.get() + kWindow;
-            std::vector<uint8_t> lut(65536);
-            for (size_t v = 0; v < 256; ++v) lut[v] = (uint8_t)v;
-            memcpy(lut.data() + kPlaceholder, c.window.data(), kWindow);
-            const uint8_t* w = lut.data();
-            uint8_t* dst = c.bytes.data();
-            // resolve and checksum block by block, while the bytes are still in cache
-            for (Segment& sg : c.segs) {
-                uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
-                for (size_t p = sg.begin; p < sg.end;) {
-                    const size_t m = std::min<size_t>(sg.end - p, 65536);
-                    resolve_symbols(sym + p, m, w, dst + p);
-                    crc = hast_crc32(crc, dst + p, m);
-                    p += m;
-                }
-                sg.crc_got = crc;
-            }
-        });
-        t_ph[3] += now() - tp; tp = now();
-        // 3c: member checks and hand-over, in stream order
+        // member checks and hand-over, in stream order
+        uint64_t m_out = member_out_checked_;
         for (size_t ci : chain) {
-            Chunk& c = chunks[ci];
-            if (!c.at_file_start && c.max_reach > std::min<uint64_t>(member_out, kWindow)) { finish("invalid distance too far back"); return; }
+            Chunk& c = b.chunks[ci];
             for (const Segment& s : c.segs) {
-                const uint64_t len = s.end - s.begin;
-                crc_run = (uint32_t)crc32_combine(crc_run, s.crc_got, (z_off_t)len);
-                member_out += len;
+                if (s.starts_member) { crc_run = (uint32_t)crc32(0L, Z_NULL, 0); m_out = 0; }
+                crc_run = (uint32_t)crc32_combine(crc_run, s.crc_got, (z_off_t)s.out_len);
+                m_out += s.out_len;
                 if (s.member_end) {
                     if (crc_run != s.crc) { finish("incorrect data check"); return; }
-                    if ((uint32_t)(member_out & 0xFFFFFFFFu) != s.isize) { finish("incorrect length check"); return; }
+                    if ((uint32_t)(m_out & 0xFFFFFFFFu) != s.isize) { finish("incorrect length check"); return; }
                     crc_run = (uint32_t)crc32(0L, Z_NULL, 0);
-                    member_out = 0;
+                    m_out = 0;
                 }
             }
-            push(std::move(c.bytes));
+            push(Piece{std::move(c.bytes), kWindow, c.n_out});
         }
-        t_ph[4] += now() - tp;
+        member_out_checked_ = m_out;
+        t_ph[3] += now() - tp;
         if (eof) { finish(""); return; }
-        if (last.end_bit >= n_bits) { finish("unexpected end of file"); return; }   // ran out of input inside a member
-        next_start = last.end_bit;
-        at_file_start = false;
+        cur ^= 1;
     }
 }
 
