@@ -716,7 +716,7 @@ def leg_cfg3(args, R):
         for b in batches:
             eng.submit_batch_device(*b)
         if collect:
-            return eng.finish(nb, want_counts=(rank == 0))
+            return eng.finish(nb, want_counts=(rank == 0), pinned=True)
 
     steps = args.cfg3_steps
     for _ in range(2):

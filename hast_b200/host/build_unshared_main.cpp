@@ -454,9 +454,10 @@ int main(int argc, char** argv) {
     // needs every partition before any list can be cut.  With one pass per sweep the table is kept.
     struct Files { const std::vector<std::string>* v; int parent; };
     const Files inputs[2] = {{&o.paternal, 0}, {&o.maternal, 1}};
-    const long passes = parts / n_gpu;
 
     for (int attempt = 0;; ++attempt) {
+        // every GPU owns one partition per pass: recomputed per attempt, a retry may have raised `parts`
+        const long passes = parts / n_gpu;
         bool full = false;
         for (auto& h : histo) h.assign(kHigh + 2, 0);
         for (auto& l : lists) l.clear();

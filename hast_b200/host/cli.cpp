@@ -38,6 +38,7 @@ void print_usage() {
           "        --partition-reads               also write NAME.{paternal,maternal,homozygous,nobarcode}.fastq\n"
           "                                        and filter_reads.log for every --read (quartering_fastq.awk).\n"
           "        --outdir DIR                    where those extra files go (default: current directory).\n"
+          "        (reads of up to 24560 bases; a longer read stops the run with its name.)\n"
           "\n"
           "Examples:\n"
           "    ./classify --hap0 p.kmers --hap1 m.kmers --read input.fastq.gz\n"

@@ -7,8 +7,10 @@
 // follows it as the sequence line, even an empty string (which the reference
 // then dies on in chopRead2Kmer, kmer.h:171; here the device flags it and
 // hast_finish fails).
+#include <algorithm>
 #include <cstring>
 #include <immintrin.h>
+#include <string>
 #include <vector>
 
 #include "host.h"
@@ -104,6 +106,11 @@ size_t newline_index(const char* p, size_t n, std::vector<uint32_t>& nl, size_t 
     return k - at;
 }
 
+// Longest read the device path takes: the smaller pass of the fused kernels (FusedSmem<true>::kCap = 24576 bases with
+// TMA staging, 40960 without) minus its 16-byte alignment slack.  Checked here so that an over-long read stops the run
+// at once, with its name, instead of after all input has been streamed (hast_finish would report it too).
+static constexpr size_t kMaxReadBases = 24560;
+
 bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out, size_t* resume) {
     const bool packed = out.packed != nullptr;
     size_t n_words = 0;
@@ -158,6 +165,11 @@ bool parse_block(const TextBlock& blk, BarcodeIndex& index, Batch& out, size_t* 
             if (n == 0 || !resume) { out.error = "FASTQ record larger than the batch buffers (raise HAST_BLOCK_MB)"; return false; }
             *resume = skip + (size_t)(head - base);
             break;
+        }
+        if (slen > kMaxReadBases) {                       // one pass of the fused kernel holds a read whole (csrc/fused.cuh)
+            out.error = "read '" + std::string(head, std::min<size_t>(hlen, 200)) + "' has " + std::to_string(slen) +
+                        " bases; this build handles reads up to " + std::to_string(kMaxReadBases) + " bases";
+            return false;
         }
         size_t bs, bl;
         parse_name(head, hlen, bs, bl);                   // classify.cpp:112-119

@@ -135,6 +135,13 @@ def test_tiny_records_fill_a_batch_before_the_block_ends(tmp_path):
     assert parse_only([tmp_path / "t.fq"], threads=2, serial=True) == want
 
 
+def test_over_long_read_stops_the_run_with_its_name(tmp_path):
+    """a read longer than one pass of the fused kernel is reported at once, by name."""
+    (tmp_path / "l.fq").write_bytes(b"@ok#1_1_1/1\nACGT\n+\nFFFF\n@giant#2_2_2/1\n" + b"ACGT" * 7000 + b"\n+\n" + b"F" * 28000 + b"\n")
+    r = run([CLASSIFY, "--hap0", "x", "--hap1", "y", "--read", tmp_path / "l.fq"], env=dict(os.environ, HAST_PARSE_ONLY="1"))
+    assert r.returncode == 1 and b"@giant#2_2_2/1" in r.stderr and b"28000 bases" in r.stderr
+
+
 def test_output_order_is_bytewise(tmp_path):
     # std::map<std::string>: "0_0_0" < "10_1_1" < "1_2_3" because '0' (0x30) < '_' (0x5F)  (SURVEY A.8)
     names = [b"1_2_3", b"10_1_1", b"0_0_0", b"Z", b"a", b"1_10_1", b"1_1_10"]

@@ -312,6 +312,27 @@ def test_cli_matches_reference_fixtures(d, tmp_path):
     assert len(first) == k
 
 
+@pytest.mark.gpu
+def test_cli_retry_with_more_partitions_counts_every_partition(tmp_path):
+    """a table-full retry that raises the partition count must sweep ALL the new partitions.  A tiny table
+    cap (HAST_KC_TABLE_MB) and an undersized --expected-distinct force the retry; the lists must equal the fixtures."""
+    d = GOLDEN[0]
+    args = []
+    for t in (d / "cmd.txt").read_text().split():
+        args.append(str(d / t) if (d / t).exists() else t)
+    r = subprocess.run([str(BIN)] + args + ["--thread", "2", "--expected-distinct", "3000"], cwd=tmp_path,
+                       capture_output=True, text=True, env=dict(os.environ, HAST_KC_TABLE_MB="1"))
+    assert r.returncode == 0, r.stdout[-800:] + r.stderr[-800:]
+    assert "count table too small, retrying" in r.stdout and "partition(s)" in r.stdout
+    n_parts = int(r.stdout.split("distinct k-mers in ")[-1].split(" partition")[0])
+    assert n_parts > 1, r.stdout[-400:]
+    for name, data in expected_files(d).items():
+        got = (tmp_path / name).read_bytes()
+        if name.endswith(".mer"):
+            got = b"".join(x + b"\n" for x in sorted(got.splitlines()))
+        assert got == data, name
+
+
 def test_cli_usage_and_errors(tmp_path):
     if not BIN.exists():
         pytest.skip("bin/build_unshared_kmers not built")

@@ -97,6 +97,25 @@ def test_restatement_matches_reference_binary(tmp_path):
         assert b"haplotype0" in r.stdout and b"haplotype1" in r.stdout and b"ambiguous" in r.stdout
 
 
+def test_reference_matches_odd_kmer_lines_as_strings(tmp_path):
+    """The one documented divergence of bin/classify_seq, pinned from the reference's side: its string sets accept ANY
+    line (03.mkoutput_by_fabulous2.0/src_main/classify.cpp:52-72), so a k-mer holding 'N' or lower case scores the
+    sequences that contain exactly that text.  The restatement reproduces it; bin/classify_seq refuses such a list
+    with an error (test_classify_seq_rejects_lists_it_cannot_represent) instead of silently scoring differently."""
+    if not REF.exists():
+        pytest.skip("oracle/_ref/classify03 not built (no /root/reference here)")
+    pat, mat, text = make_case(21)
+    odd = b"ACGTNACGTACGTACGTACGT"
+    low = b"acgtacgtacgtacgtacgta"
+    text += b">with_odd\n" + b"TT" + odd + b"GG" + low + b"CC\n"
+    r = run(REF, tmp_path, pat + odd + b"\n" + low + b"\n", mat, text, "fasta")
+    assert r.returncode == 0
+    assert r.stdout == s3.classify(pat + odd + b"\n" + low + b"\n", mat, text, "fasta")
+    row = [ln for ln in r.stdout.splitlines() if ln.startswith(b"with_odd")]
+    base = run(REF, tmp_path, pat, mat, text, "fasta").stdout
+    assert row and row != [ln for ln in base.splitlines() if ln.startswith(b"with_odd")]     # the odd lines did score
+
+
 @pytest.mark.parametrize("args", [[], ["--hap", "a", "--read", "r"], ["--hap", "a", "--hap", "b"], ["-h"],
                                   ["--hap", "a", "--hap", "b", "--read", "r", "--format", "bam"]])
 def test_usage_exit_code(args):
