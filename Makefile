@@ -37,7 +37,7 @@ $(SYNTH_CUDA): hast_b200/tools/synth_gen.cu hast_b200/tools/synth_gen.h
 	@mkdir -p hast_b200/lib
 	$(NVCC) $(NVFLAGS) -shared $< -o $@
 
-host: bin/classify bin/mergeResult bin/quartering_fastq bin/classify_seq bin/build_unshared_kmers bin/hast_gunzip
+host: bin/classify bin/mergeResult bin/quartering_fastq bin/classify_seq bin/build_unshared_kmers bin/hast_gunzip bin/h2d_probe
 HOST_SRCS := $(wildcard $(HOST)/*.cpp)
 HOST_HDRS := $(wildcard $(HOST)/*.h)
 MAINS := $(HOST)/merge_result_main.cpp $(HOST)/quartering_main.cpp $(HOST)/classify_main.cpp $(HOST)/classify_seq_main.cpp $(HOST)/build_unshared_main.cpp $(HOST)/gunzip_main.cpp
@@ -63,6 +63,10 @@ bin/quartering_fastq: $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/
 bin/hast_gunzip: $(HOST)/gunzip_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate_par.cpp $(HOST)/inflate.h $(HOST)/crc32_clmul.h $(HOST)/inflate_par.h
 	@mkdir -p bin
 	$(CXX) -O2 -g -std=c++17 -Wall -pthread $(HOST)/gunzip_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate_par.cpp -lz -o $@
+# measurement tool: the box's host->device ceiling with 1/2/4/8 GPUs copying at once
+bin/h2d_probe: hast_b200/tools/h2d_probe.cu
+	@mkdir -p bin
+	$(NVCC) $(ARCH) -O2 -std=c++17 -Xcompiler -pthread $< -o $@
 bin/mergeResult: $(HOST)/merge_result_main.cpp
 	@mkdir -p bin
 	$(CXX) -O2 -g -std=c++17 -Wall $< -o $@

@@ -5,7 +5,7 @@ H2D, classify, reduce, print the table) next to the untouched reference binary o
     python profiles/tools/bench_cli.py [--pairs 4000000] [--gpus 1] > out.json
 
 Workload: the configs[1] trio (100 Mbp, k=21) with the first `pairs` read pairs written as child.r1/r2 FASTQ,
-plain and gzip (level 6, `gzip -6`: what sequencers ship).  Legs: plain / gz through the readers' own decoder /
+plain and gzip (ONE member per file, level 6: what sequencers ship).  Legs: plain / gz through the readers' own decoder /
 gz through zlib (HAST_ZLIB=1) / the reference binary (oracle/_ref/classify_O2, best --thread) on the gz files.
 Reported per leg: wall seconds of the whole process and pairs/s; for bin/classify also the streaming phase alone
 (--stats-json).  Output tables are compared byte for byte.
@@ -55,10 +55,7 @@ def main():
         d = Path(d)
         pat, mat = trio.write_kmer_lists(d)
         r1, r2 = trio.write_fastq(d, gz=False)
-        gz = []
-        for p in (r1, r2):                                     # gzip -6 like a sequencer's output
-            subprocess.run(["gzip", "-6", "-k", p], check=True)
-            gz.append(p + ".gz")
+        gz = list(trio.write_fastq(d / "gz", gz=6))            # one gzip member per file, level 6, like a sequencer's output
         out["fastq_bytes"] = os.path.getsize(r1) + os.path.getsize(r2)
         out["gz_bytes"] = sum(os.path.getsize(p) for p in gz)
         exe = str(ROOT / "bin" / "classify")
