@@ -58,7 +58,7 @@ bin/build_unshared_kmers: $(HOST)/build_unshared_main.cpp $(HOST)/inflate.cpp $(
 # the read partitioner alone needs no GPU and no CUDA library
 bin/quartering_fastq: $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/fastq_source.cpp $(HOST_HDRS)
 	@mkdir -p bin
-	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/fastq_source.cpp $(HOST)/inflate.cpp $(HOST)/inflate_par.cpp -lz -o $@
+	$(CXX) -O2 -g -std=c++17 -Wall -pthread -Iinclude $(HOST)/quartering_main.cpp $(HOST)/partition.cpp $(HOST)/fastq_source.cpp $(HOST)/plain_slicer.cpp $(HOST)/parser.cpp $(HOST)/barcode_index.cpp $(HOST)/inflate.cpp $(HOST)/inflate_par.cpp -lz -o $@
 # the gzip decoder of the readers as a stand-alone tool (tests, timing)
 bin/hast_gunzip: $(HOST)/gunzip_main.cpp $(HOST)/inflate.cpp $(HOST)/inflate_par.cpp $(HOST)/inflate.h $(HOST)/crc32_clmul.h $(HOST)/inflate_par.h
 	@mkdir -p bin

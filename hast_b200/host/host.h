@@ -167,8 +167,9 @@ std::string write_barcode_lists(const std::string& dir, const std::vector<std::s
                                 const int32_t* counts, uint64_t counts_out[3], BarcodeLists* lists);
 // quartering_fastq.awk over one FASTQ(.gz | "-"): PREFIX.{paternal,maternal,homozygous,nobarcode}.fastq
 // and filter_reads.log (appended) in outdir ("" = cwd).  display_name is awk's FILENAME.
+// threads <= 0: all cores (at most 16)
 std::string partition_fastq(const std::string& input, const std::string& display_name, const std::string& prefix,
-                            const std::string& outdir, const BarcodeLists& lists, PartitionStats& st);
+                            const std::string& outdir, const BarcodeLists& lists, PartitionStats& st, int threads = 0);
 std::string partition_prefix(const std::string& path);       // basename, ".gz" stripped (:178-180)
 
 // ---- the pipeline ---------------------------------------------------------------

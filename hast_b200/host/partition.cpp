@@ -34,6 +34,7 @@
 
 #include "fastq_source.h"
 #include "host.h"
+#include "plain_slicer.h"
 
 namespace hasthost {
 
@@ -247,123 +248,242 @@ std::string write_barcode_lists(const std::string& dir, const std::vector<std::s
     return "";
 }
 
-// quartering_fastq.awk on one input file
-std::string partition_fastq(const std::string& input, const std::string& display_name, const std::string& prefix,
-                            const std::string& outdir, const BarcodeLists& lists, PartitionStats& st) {
-    st = PartitionStats{};
-    FastqSource src;
-    std::string err = src.open(input);
-    if (!err.empty()) return err;
-    const std::string base = outdir.empty() ? prefix : outdir + "/" + prefix;
-    OutFile out[4] = {OutFile(base + ".nobarcode.fastq"), OutFile(base + ".paternal.fastq"),
-                      OutFile(base + ".maternal.fastq"), OutFile(base + ".homozygous.fastq")};
+// quartering_fastq.awk on one input file, on several threads.
+//
+// The awk program is a serial pass; here blocks of whole records (plain files: slices of the mapping,
+// plain_slicer.h; gzip / pipes: what the reader thread inflates) are routed by `threads` workers into four private
+// buffers each, and committed in input order: a short critical section hands every block its byte offsets in the
+// four output files (and adds up the statistics and the "unclassify barcode" messages, in order), the bytes
+// themselves are then written with pwrite() by all workers at once.  The files come out byte-identical to awk's.
+namespace {
 
-    // reader thread: read / inflate the next block while this one is routed
-    TextBlock blocks[3];
-    std::mutex mu;
-    std::condition_variable cv;
-    std::deque<int> ready, free_ids{0, 1, 2};
-    bool done = false;
-    std::string rerr;
-    std::thread reader([&] {
-        for (;;) {
-            int id;
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return !free_ids.empty() || done; });
-                if (done) return;
-                id = free_ids.front();
-                free_ids.pop_front();
-            }
-            std::string e;
-            const bool more = src.next(blocks[id], (size_t)16 << 20, e);
-            std::lock_guard<std::mutex> lk(mu);
-            if (!e.empty()) rerr = e;
-            if (!more || !e.empty()) { done = true; cv.notify_all(); return; }
-            ready.push_back(id);
-            cv.notify_all();
-        }
-    });
+struct Routed {
+    std::vector<char> buf[4];
+    PartitionStats st;
+    std::string msgs;
+    bool any_line = false;
+};
 
+// one block of whole records -> r (quartering_fastq.awk:22-55)
+void route_block(const char* p, size_t len, const BarcodeLists& lists, Routed& r) {
+    for (auto& b : r.buf) b.clear();
+    r.st = PartitionStats{};
+    r.msgs.clear();
+    r.any_line = len > 0;
     uint64_t fnr = 0;
     int type = 0;          // awk: uninitialised read_type compares equal to 0; set before use anyway
-    bool ok = true;
-    std::string werr;
-    for (;;) {
-        int id;
-        {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return !ready.empty() || done; });
-            if (ready.empty()) break;
-            id = ready.front();
-            ready.pop_front();
-        }
-        const char* p = blocks[id].data.data();
-        const size_t len = blocks[id].len;
-        size_t s = 0;
-        while (s < len && ok) {
-            const char* nl = (const char*)memchr(p + s, '\n', len - s);
-            const size_t e = nl ? (size_t)(nl - p) : len;          // an unterminated last line is a record too
-            ++fnr;
-            if (fnr % 4 == 1) {                                    // quartering_fastq.awk:22
-                ++st.total;
-                const char* h = p + s;
-                const size_t hl = e - s;
-                const size_t a = first_sep(h, hl);
-                if (a < hl) {                                      // NF > 1
-                    const size_t b = a + 1 + first_sep(h + a + 1, hl - a - 1);
-                    const char* key = h + a + 1;
-                    const size_t kl = b - a - 1;
-                    if (kl == 5 && memcmp(key, "0_0_0", 5) == 0) {
-                        ++st.no_barcode; type = 0;
-                    } else {
-                        const int t = lists.find(key, kl);
-                        if (t == BarcodeLists::kPaternal) { ++st.paternal; type = 1; }
-                        else if (t == BarcodeLists::kMaternal) { ++st.maternal; type = 2; }
-                        else if (t == BarcodeLists::kHomozygous) { ++st.homozygous; type = 3; }
-                        else {
-                            fprintf(stderr, "ERROR : unclassify barcode : %.*s\n", (int)kl, key);
-                            ++st.unclassified; type = -1;
-                        }
-                    }
+    size_t s = 0;
+    while (s < len) {
+        const char* nl = (const char*)memchr(p + s, '\n', len - s);
+        const size_t e = nl ? (size_t)(nl - p) : len;          // an unterminated last line is a record too
+        ++fnr;
+        if (fnr % 4 == 1) {                                    // quartering_fastq.awk:22
+            ++r.st.total;
+            const char* h = p + s;
+            const size_t hl = e - s;
+            const size_t a = first_sep(h, hl);
+            if (a < hl) {                                      // NF > 1
+                const size_t b = a + 1 + first_sep(h + a + 1, hl - a - 1);
+                const char* key = h + a + 1;
+                const size_t kl = b - a - 1;
+                if (kl == 5 && memcmp(key, "0_0_0", 5) == 0) {
+                    ++r.st.no_barcode; type = 0;
                 } else {
-                    ++st.no_barcode; type = 0;
+                    const int t = lists.find(key, kl);
+                    if (t == BarcodeLists::kPaternal) { ++r.st.paternal; type = 1; }
+                    else if (t == BarcodeLists::kMaternal) { ++r.st.maternal; type = 2; }
+                    else if (t == BarcodeLists::kHomozygous) { ++r.st.homozygous; type = 3; }
+                    else {
+                        r.msgs += "ERROR : unclassify barcode : ";
+                        r.msgs.append(key, kl);
+                        r.msgs += '\n';
+                        ++r.st.unclassified; type = -1;
+                    }
+                }
+            } else {
+                ++r.st.no_barcode; type = 0;
+            }
+        }
+        if (type >= 0) {
+            std::vector<char>& o = r.buf[type];
+            o.insert(o.end(), p + s, p + e);
+            o.push_back('\n');                                 // ORS
+        }
+        s = e + 1;
+    }
+}
+
+bool pwrite_all(int fd, const char* p, size_t n, uint64_t off, std::string& err, const std::string& path) {
+    while (n) {
+        const ssize_t w = ::pwrite(fd, p, n, (off_t)off);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            err = "write to " + path + " failed: " + strerror(errno);
+            return false;
+        }
+        p += w; n -= (size_t)w; off += (uint64_t)w;
+    }
+    return true;
+}
+
+}  // namespace
+
+std::string partition_fastq(const std::string& input, const std::string& display_name, const std::string& prefix,
+                            const std::string& outdir, const BarcodeLists& lists, PartitionStats& st, int threads) {
+    st = PartitionStats{};
+    if (threads <= 0) threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const std::string base = outdir.empty() ? prefix : outdir + "/" + prefix;
+    const std::string paths[4] = {base + ".nobarcode.fastq", base + ".paternal.fastq", base + ".maternal.fastq",
+                                  base + ".homozygous.fastq"};
+    // input: slices of a mapped plain file, or blocks from a reader thread
+    const size_t n_in = input.size();
+    const bool gz = n_in > 3 && input.compare(n_in - 3, 3, ".gz") == 0;
+    PlainSlicer slicer;
+    bool sliced = false;
+    if (!gz && input != "-" && !getenv("HAST_SERIAL_READER")) {
+        size_t slice_bytes = (size_t)4 << 20;
+        if (const char* sb = getenv("HAST_SLICE_BYTES")) slice_bytes = (size_t)std::max(1L, atol(sb));
+        const std::string e = slicer.open(input, slice_bytes);
+        if (!e.empty()) return e;
+        sliced = slicer.usable();
+    }
+    FastqSource src;
+    if (!sliced) {
+        const std::string e = src.open(input, std::max(1, std::min(8, threads / 2)));
+        if (!e.empty()) return e;
+    }
+
+    std::mutex mu;
+    std::condition_variable cv;
+    // reader-thread mode
+    const size_t n_blocks = (size_t)threads + 2;
+    std::vector<TextBlock> blocks(sliced ? 0 : n_blocks);
+    std::deque<std::pair<size_t, uint64_t>> ready;             // (block id, sequence number)
+    std::deque<size_t> free_ids;
+    for (size_t i = 0; i < blocks.size(); ++i) free_ids.push_back(i);
+    bool read_done = sliced, failed = false;
+    std::string rerr, werr;
+    // ordered commit
+    uint64_t next_seq = 0, off[4] = {0, 0, 0, 0}, text_bytes = 0;
+    int fds[4] = {-1, -1, -1, -1};
+    bool any_line = false;
+
+    std::thread reader;
+    if (!sliced)
+        reader = std::thread([&] {
+            uint64_t seq = 0;
+            for (;;) {
+                size_t id;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return !free_ids.empty() || failed; });
+                    if (failed) break;
+                    id = free_ids.front();
+                    free_ids.pop_front();
+                }
+                std::string e;
+                const bool more = src.next(blocks[id], (size_t)8 << 20, e);
+                std::lock_guard<std::mutex> lk(mu);
+                if (!e.empty()) { rerr = e; failed = true; }
+                if (!more || !e.empty()) break;
+                ready.emplace_back(id, seq++);
+                cv.notify_all();
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            read_done = true;
+            cv.notify_all();
+        });
+
+    auto worker = [&] {
+        Routed r;
+        TextBlock own;
+        for (;;) {
+            const char* p = nullptr;
+            size_t len = 0, id = 0;
+            uint64_t seq = 0;
+            if (sliced) {
+                if (!slicer.next(own, nullptr, &seq)) break;
+                p = own.text();
+                len = own.len;
+            } else {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !ready.empty() || read_done || failed; });
+                if (failed || ready.empty()) break;
+                id = ready.front().first;
+                seq = ready.front().second;
+                ready.pop_front();
+                p = blocks[id].text();
+                len = blocks[id].len;
+            }
+            route_block(p, len, lists, r);
+            uint64_t my_off[4];
+            bool stop = false;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return next_seq == seq || failed; });
+                if (failed) stop = true;
+                else {
+                    for (int i = 0; i < 4 && !stop; ++i) {
+                        my_off[i] = off[i];
+                        if (r.buf[i].empty()) continue;
+                        if (fds[i] < 0) {                          // awk's `print > file`: created on first use
+                            fds[i] = ::open(paths[i].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+                            if (fds[i] < 0) { werr = "cannot open " + paths[i] + " for writing: " + strerror(errno); failed = stop = true; }
+                        }
+                        off[i] += r.buf[i].size();
+                    }
+                    if (!r.msgs.empty()) fwrite(r.msgs.data(), 1, r.msgs.size(), stderr);
+                    st.total += r.st.total; st.no_barcode += r.st.no_barcode; st.paternal += r.st.paternal;
+                    st.maternal += r.st.maternal; st.homozygous += r.st.homozygous; st.unclassified += r.st.unclassified;
+                    any_line |= r.any_line;
+                    text_bytes += len;
+                    ++next_seq;
+                }
+                if (!sliced) free_ids.push_back(id);
+                cv.notify_all();
+            }
+            if (stop) break;
+            for (int i = 0; i < 4; ++i) {
+                std::string e;
+                if (!r.buf[i].empty() && !pwrite_all(fds[i], r.buf[i].data(), r.buf[i].size(), my_off[i], e, paths[i])) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (werr.empty()) werr = e;
+                    failed = true;
+                    cv.notify_all();
                 }
             }
-            if (type >= 0 && !out[type].put(p + s, e - s)) { ok = false; werr = out[type].error(); }
-            s = e + 1;
         }
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            free_ids.push_back(id);
-            if (!ok) done = true;
-            cv.notify_all();
-        }
-        if (!ok) break;
-    }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
     {
         std::lock_guard<std::mutex> lk(mu);
-        done = true;
+        if (!read_done) failed = failed || !werr.empty();
         cv.notify_all();
     }
-    reader.join();
-    for (auto& o : out)
-        if (!o.close() && ok) { ok = false; werr = o.error(); }
+    if (reader.joinable()) {
+        { std::lock_guard<std::mutex> lk(mu); if (!werr.empty()) failed = true; cv.notify_all(); }
+        reader.join();
+    }
+    for (int i = 0; i < 4; ++i)
+        if (fds[i] >= 0 && ::close(fds[i]) != 0 && werr.empty()) werr = "close of " + paths[i] + " failed: " + strerror(errno);
     if (!rerr.empty()) return rerr;
-    if (!ok) return werr;
+    if (!werr.empty()) return werr;
 
     // filter_reads.log (quartering_fastq.awk:19-21,56-61), appended
     const std::string logp = outdir.empty() ? "filter_reads.log" : outdir + "/filter_reads.log";
     FILE* lg = fopen(logp.c_str(), "ab");
     if (!lg) return "cannot open " + logp;
-    if (fnr > 0) fprintf(lg, "%s\n", display_name.c_str());
+    if (any_line) fprintf(lg, "%s\n", display_name.c_str());
     fprintf(lg, "#Total reads                : %llu \n", (unsigned long long)st.total);
     fprintf(lg, "#Reads without barcode      : %llu \n", (unsigned long long)st.no_barcode);
     fprintf(lg, "#Paternal reads             : %llu \n", (unsigned long long)st.paternal);
     fprintf(lg, "#Maternal reads             : %llu \n", (unsigned long long)st.maternal);
     fprintf(lg, "#Homozygous reads           : %llu \n", (unsigned long long)st.homozygous);
     fclose(lg);
-    st.text_bytes = src.bytes_out();
+    st.text_bytes = text_bytes;
     return "";
 }
 

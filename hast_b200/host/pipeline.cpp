@@ -502,7 +502,7 @@ int run_classify(const Options& opt, RunStats& st) {
                 PartitionStats ps;
                 // the script pipes gzip input into `awk ... -`, whose FILENAME is then "-" (:181)
                 const std::string e2 = partition_fastq(path, gz ? "-" : path, partition_prefix(path), opt.outdir,
-                                                       lists, ps);
+                                                       lists, ps, opt.threads);
                 if (!e2.empty()) { fprintf(stderr, "ERROR : %s\n", e2.c_str()); return 1; }
                 st.partition_text_bytes += ps.text_bytes;
             }

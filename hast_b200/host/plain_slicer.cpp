@@ -39,9 +39,10 @@ std::string PlainSlicer::open(const std::string& path, size_t slice_bytes) {
     return "";
 }
 
-bool PlainSlicer::next(TextBlock& blk, bool* first) {
+bool PlainSlicer::next(TextBlock& blk, bool* first, uint64_t* index) {
     const uint64_t i = next_.fetch_add(1, std::memory_order_relaxed);
     if (first) *first = i == 0;
+    if (index) *index = i;
     if (i >= n_slices_) return false;
     const uint64_t a = i * slice_, b = std::min(size_, a + slice_);
     const size_t n = (size_t)(b - a);

@@ -33,7 +33,8 @@ public:
     // Claims the next slice and points blk (view / len / nl) at the whole records that END in it; blk.len may be
     // 0 (no record ends inside the slice).  Returns false when every slice has been claimed.  Thread safe.
     // first is set for the call that claimed slice 0.
-    bool next(TextBlock& blk, bool* first = nullptr);
+    // index (optional) receives the slice number: blocks of consecutive indices are consecutive in the file.
+    bool next(TextBlock& blk, bool* first = nullptr, uint64_t* index = nullptr);
 private:
     static constexpr uint64_t kNotRegular = ~0ull;
     struct Hand {                         // what slice i needs from slices 0..i-1

@@ -311,16 +311,19 @@ class StreamTrio:
         return blob[:used].tobytes(), off[:B + 1]
 
     def kmer_text(self, which: int) -> bytes:
+        """one k-mer per line, orientation chosen by a hash of the k-mer (the reference canonicalises on load)"""
+        from .synth import revcomp_packed
         km = self.pat if which == 0 else self.mat
         k = self.spec.k
         flip = (tmix(torch.from_numpy(km.view(np.int64)) ^ 77).numpy() & 1).astype(bool)
-        from .synth import revcomp_packed
         km = np.where(flip, revcomp_packed(km, k), km)
-        out = np.empty((km.size, k + 1), np.uint8)
+        t = torch.from_numpy(km.view(np.int64)).to(self.device)
+        lut = torch.from_numpy(LETTERS.copy()).to(self.device)
+        out = torch.empty((t.numel(), k + 1), dtype=torch.uint8, device=self.device)
         for j in range(k):
-            out[:, j] = LETTERS[((km >> np.uint64(2 * (k - 1 - j))) & np.uint64(3)).astype(np.intp)]
+            out[:, j] = lut[(t >> (2 * (k - 1 - j))) & 3]
         out[:, k] = ord("\n")
-        return out.tobytes()
+        return out.cpu().numpy().tobytes()
 
     def write_kmer_lists(self, outdir):
         outdir = Path(outdir)

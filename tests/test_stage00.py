@@ -320,8 +320,8 @@ def test_cli_retry_with_more_partitions_counts_every_partition(tmp_path):
     args = []
     for t in (d / "cmd.txt").read_text().split():
         args.append(str(d / t) if (d / t).exists() else t)
-    r = subprocess.run([str(BIN)] + args + ["--thread", "2", "--expected-distinct", "3000"], cwd=tmp_path,
-                       capture_output=True, text=True, env=dict(os.environ, HAST_KC_TABLE_MB="1"))
+    r = subprocess.run([str(BIN)] + args + ["--thread", "2", "--expected-distinct", "300"], cwd=tmp_path,
+                       capture_output=True, text=True, env=dict(os.environ, HAST_KC_TABLE_MB="0"))
     assert r.returncode == 0, r.stdout[-800:] + r.stderr[-800:]
     assert "count table too small, retrying" in r.stdout and "partition(s)" in r.stdout
     n_parts = int(r.stdout.split("distinct k-mers in ")[-1].split(" partition")[0])
