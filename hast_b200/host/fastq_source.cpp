@@ -103,7 +103,68 @@ size_t FastqSource::raw_read(char* dst, size_t n, std::string& err) {
     }
 }
 
+// Parallel decoder: its output pieces are handed on as they are (no copy).  A record that straddles two pieces is
+// made contiguous by writing the tail of the previous piece into the free space in front of the next one; the
+// pass that finds the record boundary also builds the newline index the parser needs.
+bool FastqSource::next_from_pieces(TextBlock& blk, std::string& err) {
+    blk.hold.reset();
+    blk.view = nullptr;
+    blk.begin = 0;
+    blk.has_nl = false;
+    blk.last_of_file = false;
+    for (;;) {
+        uint8_t* data = nullptr;
+        size_t n = 0;
+        std::shared_ptr<void> hold;
+        if (!pinf_->next_owned(&data, &n, &hold)) {
+            if (!pinf_->error().empty()) { err = "inflate failed on " + path_ + ": " + pinf_->error(); return false; }
+            eof_ = true;
+            if (carry_.empty()) return false;
+            blk.data.assign(carry_.begin(), carry_.end());    // what is left: at most a partial record
+            blk.len = carry_.size();
+            blk.last_of_file = true;
+            bytes_out_ += blk.len;
+            carry_.clear();
+            return true;
+        }
+        char* base;
+        size_t len;
+        if (carry_.size() <= ParallelGzip::kFront) {
+            base = reinterpret_cast<char*>(data) - carry_.size();
+            if (!carry_.empty()) memcpy(base, carry_.data(), carry_.size());
+            len = carry_.size() + n;
+        } else {                                              // records larger than the front space: the copying way
+            blk.data.resize(carry_.size() + n);
+            memcpy(blk.data.data(), carry_.data(), carry_.size());
+            memcpy(blk.data.data() + carry_.size(), data, n);
+            hold.reset();
+            base = blk.data.data();
+            len = carry_.size() + n;
+        }
+        if (len > 0xFFFFFFFFull) { err = "FASTQ record larger than 4 GiB in " + path_; return false; }
+        const size_t c = newline_index(base, len, blk.nl, 0);
+        const size_t whole = c & ~(size_t)3;                  // newlines that close whole records
+        if (!whole) {                                         // not one whole record yet: keep everything, read on
+            carry_.assign(base, base + len);
+            continue;
+        }
+        const size_t cut = (size_t)blk.nl[whole - 1] + 1;
+        carry_.assign(base + cut, base + len);
+        if (hold) { blk.view = base; blk.hold = std::move(hold); }
+        blk.len = cut;
+        blk.nl_begin = 0;
+        blk.nl_count = whole;
+        blk.has_nl = true;
+        bytes_out_ += cut;
+        return true;
+    }
+}
+
 bool FastqSource::next(TextBlock& blk, size_t target, std::string& err) {
+    if (pinf_ && !getenv("HAST_GZ_COPY")) return next_from_pieces(blk, err);
+    blk.hold.reset();
+    blk.view = nullptr;
+    blk.has_nl = false;
     if (eof_ && carry_.empty()) return false;
     size_t cap = std::max(blk.data.size(), target + carry_.size() + 4096);
     blk.data.resize(cap);

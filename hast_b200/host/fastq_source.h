@@ -32,6 +32,7 @@ public:
     uint64_t bytes_out() const { return bytes_out_; }
 private:
     size_t raw_read(char* dst, size_t n, std::string& err);
+    bool next_from_pieces(TextBlock& blk, std::string& err);
     std::string path_;
     gzFile gz_ = nullptr;
     std::unique_ptr<GzipInflater> inf_;

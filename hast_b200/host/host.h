@@ -86,6 +86,7 @@ struct TextBlock {
     std::vector<uint32_t> nl;
     size_t nl_begin = 0, nl_count = 0;
     bool has_nl = false;
+    std::shared_ptr<void> hold;  // keeps the memory behind `view` alive (a decoder's output buffer); reset() when parsed
     const char* text() const { return view ? view : data.data() + begin; }
 };
 // Offsets of every '\n' in p[0, n), appended to out from index `at` on (out is grown as needed); returns the

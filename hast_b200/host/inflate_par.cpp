@@ -626,23 +626,23 @@ void ParallelGzip::start() { coord_ = std::thread([this] { run(); }); }
 // Sizes are rounded up generously so that a recycled buffer nearly always fits the next chunk.
 ParallelGzip::Buffer ParallelGzip::take_buffer(size_t need) {
     {
-        std::lock_guard<std::mutex> lk(mu_);
-        for (size_t i = spare_.size(); i-- > 0;)
-            if (spare_[i].cap >= need) {
-                Buffer b = std::move(spare_[i]);
-                spare_.erase(spare_.begin() + (long)i);
+        std::lock_guard<std::mutex> lk(pool_->mu);
+        std::vector<Buffer>& spare = pool_->spare;
+        for (size_t i = spare.size(); i-- > 0;)
+            if (spare[i].cap >= need) {
+                Buffer b = std::move(spare[i]);
+                spare.erase(spare.begin() + (long)i);
                 return b;
             }
-        if (spare_.size() >= 8) spare_.erase(spare_.begin());  // none fits: let the oldest small one go
+        if (spare.size() >= 8) spare.erase(spare.begin());     // none fits: let the oldest small one go
     }
-    if (getenv("HAST_PAR_PROF")) fprintf(stderr, "fresh buffer for %zu bytes\n", need);
     return Buffer(std::max<size_t>(need + need / 2, (size_t)8 << 20));
 }
 
 void ParallelGzip::recycle(Buffer&& b) {
     if (!b.cap) return;
-    std::lock_guard<std::mutex> lk(mu_);
-    if (spare_.size() < 64) spare_.push_back(std::move(b));
+    std::lock_guard<std::mutex> lk(pool_->mu);
+    if (pool_->spare.size() < 64) pool_->spare.push_back(std::move(b));
 }
 
 ParallelGzip::Buffer::Buffer(size_t n) {
@@ -698,13 +698,33 @@ bool ParallelGzip::next(const uint8_t** data, size_t* len) {
         err_ = err_pending_;
         return false;
     }
-    if (current_.buf.cap && spare_.size() < 64) spare_.push_back(std::move(current_.buf));
+    Buffer old = std::move(current_.buf);
     current_ = std::move(ready_.front());
     ready_.pop_front();
     ready_bytes_ -= current_.len;
     cv_room_.notify_one();
+    lk.unlock();
+    recycle(std::move(old));
     *data = current_.buf.p + current_.off;
     *len = current_.len;
+    return true;
+}
+
+bool ParallelGzip::next_owned(uint8_t** data, size_t* len, std::shared_ptr<void>* hold) {
+    const uint8_t* p;
+    if (!next(&p, len)) { *data = nullptr; return false; }
+    static_assert(kFront <= kWindow, "the history area in front of a piece is what the caller may overwrite");
+    *data = current_.buf.p + current_.off;
+    std::shared_ptr<BufferPool> pool = pool_;
+    *hold = std::shared_ptr<void>(new Buffer(std::move(current_.buf)), [pool](void* v) {
+        Buffer* b = static_cast<Buffer*>(v);
+        {
+            std::lock_guard<std::mutex> lk(pool->mu);
+            if (b->cap && pool->spare.size() < 64) pool->spare.push_back(std::move(*b));
+        }
+        delete b;
+    });
+    current_ = Piece{};
     return true;
 }
 

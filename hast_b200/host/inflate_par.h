@@ -48,6 +48,12 @@ public:
     bool is_gzip() const { return n_in_ >= 2 && in_[0] == 0x1F && in_[1] == 0x8B; }
     // Next piece of decompressed bytes (valid until the next call).  false at the end or on error.
     bool next(const uint8_t** data, size_t* len);
+    // The same without the copy a caller would otherwise make: the piece's buffer changes hands.  *data points at
+    // *len decoded bytes with at least kFront writable bytes in front of them (room for the tail of the previous
+    // piece, so that a record straddling two pieces can be made contiguous in place); *hold keeps the buffer alive
+    // and hands it back to this decoder's pool -- also after the decoder itself is gone -- when it is released.
+    static constexpr size_t kFront = 32768;
+    bool next_owned(uint8_t** data, size_t* len, std::shared_ptr<void>* hold);
     const std::string& error() const { return err_; }
 
     struct Stats { uint64_t chunks = 0, starts_found = 0, starts_dropped = 0, batches = 0; };
@@ -95,7 +101,8 @@ private:
     bool done_ = false, stop_ = false;
     Piece current_;
     uint64_t member_out_checked_ = 0;
-    std::vector<Buffer> spare_;                 // output buffers handed back by next(), reused by the replay
+    struct BufferPool { std::mutex mu; std::vector<Buffer> spare; };
+    std::shared_ptr<BufferPool> pool_ = std::make_shared<BufferPool>();   // output buffers handed back, reused by the replay
     std::string err_, err_pending_;
     Stats stats_;
 };

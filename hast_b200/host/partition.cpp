@@ -439,7 +439,7 @@ std::string partition_fastq(const std::string& input, const std::string& display
                     text_bytes += len;
                     ++next_seq;
                 }
-                if (!sliced) free_ids.push_back(id);
+                if (!sliced) { blocks[id].hold.reset(); free_ids.push_back(id); }
                 cv.notify_all();
             }
             if (stop) break;

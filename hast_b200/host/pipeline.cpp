@@ -309,11 +309,6 @@ int run_classify(const Options& opt, RunStats& st) {
                 while (pos < blk.len) {
                     Batch* b = nullptr;
                     if (!q_batch_free.pop(b)) return false;
-                    if (blk.len - pos + 4096 > b->cap_bases) {     // an oversized block (very long records)
-                        sh.fail("FASTQ record larger than the batch buffer; raise HAST_BLOCK_MB");
-                        abort_all();
-                        return false;
-                    }
                     if (!parse_block(blk, index, *b, &pos)) { sh.fail(b->error); abort_all(); return false; }
                     if (!q_batch.push(b)) return false;
                 }
@@ -340,6 +335,7 @@ int run_classify(const Options& opt, RunStats& st) {
             TextBlock* blk = nullptr;
             while (alive && q_text.pop(blk)) {
                 alive = parse_and_push(*blk);
+                blk->hold.reset();                                // a decoder's buffer goes back to its pool
                 q_text_free.push(blk);
             }
             if (--parsers_left == 0) q_batch.finish();
