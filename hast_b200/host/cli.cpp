@@ -31,7 +31,8 @@ void print_usage() {
           "                                        default \"TCTGCTGAGTCGAGAACGTCTCTGTGAGCCAAGGAGTTGCTCTGG\"\n"
           "\n"
           "B200 build only (long form):\n"
-          "        --gpus N                        GPUs of this box to use (default: all visible; env HAST_GPUS).\n"
+          "        --gpus N                        GPUs of this box to use (default 1; env HAST_GPUS).  One GPU classifies\n"
+          "                                        ~100x faster than the host can read FASTQ: more only add start-up time.\n"
           "        --stats-json FILE               write throughput statistics as JSON.\n"
           "        --split-barcodes                also write {paternal,maternal,homozygous}.unique.barcodes\n"
           "                                        (the three awk passes of classify_stlfr_reads.sh).\n"

@@ -24,7 +24,7 @@ struct Options {
     std::string adaptor_f = "CTGTCTCTTATACACATCTTAGGAAGACAAGCACTGACGACATGA";   // classify.cpp:312
     std::string adaptor_r = "TCTGCTGAGTCGAGAACGTCTCTGTGAGCCAAGGAGTTGCTCTGG";   // classify.cpp:313
     // extensions (long options only; the reference rejects them, so no clash)
-    int gpus = 0;                          // 0 = all visible
+    int gpus = 0;                          // 0 = default (one GPU)
     std::string stats_json;                // throughput side output
     bool split_barcodes = false;           // also write the three *.unique.barcodes lists (script :156-162)
     bool partition_reads = false;          // also partition every input FASTQ (script :176-185); implies split

@@ -120,7 +120,10 @@ int run_classify(const Options& opt, RunStats& st) {
         fprintf(stderr, "ERROR : no CUDA device found; this build of classify has no CPU path\n");
         return 1;
     }
-    int n_gpu = parse_only ? 1 : (opt.gpus > 0 ? std::min(opt.gpus, n_dev) : n_dev);
+    // One GPU by default: measured on an 8 x B200 box (profiles/bench_r02_m_cfg5.json) the host streams gzip FASTQ at
+    // 13-14 M pairs/s whether 1 or 8 GPUs classify it (one GPU's kernel takes 1500 M pairs/s), and 8 contexts cost
+    // 4 s more to set up.  --gpus N shards the batches over N GPUs for callers whose input is faster than that.
+    int n_gpu = parse_only ? 1 : std::min(opt.gpus > 0 ? opt.gpus : 1, n_dev);
     st.gpus = n_gpu;
     st.parser_threads = opt.threads;
 

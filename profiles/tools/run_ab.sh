@@ -5,7 +5,7 @@ for L in $LIBS; do
   N=$(basename $L .so)
   HAST_B200_LIB=$PWD/$L python -m pytest tests/test_gpu_parity.py -x -q -k "prefilter_mini and (fused or low_complex or saturated or packed)" > $O/${T}_${N}_pytest.log 2>&1; echo "$N pytest rc=$? $(tail -1 $O/${T}_${N}_pytest.log)"
   for W in $WS; do
-    HAST_B200_LIB=$PWD/$L python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $O/${T}_${N}_$W.json 2> $O/${T}_${N}_$W.log
+    HAST_B200_LIB=$PWD/$L python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-cfg3 > $O/${T}_${N}_$W.json 2> $O/${T}_${N}_$W.log
     python - <<P
 import json
 d=json.load(open("$O/${T}_${N}_$W.json"))
