@@ -52,8 +52,13 @@ namespace hast {
 #ifndef HAST_PASS_CAP
 #define HAST_PASS_CAP 40960
 #endif
+// Most reads a tile may hold (sizes the per-read arrays in shared memory).  The tile size itself is chosen per
+// batch (fused_reads_per_tile below): as many reads as fill one pass of HAST_PASS_CAP bytes, because the fixed
+// cost of a tile -- six CTA barriers, the stragglers each of them waits for -- is then paid once per 40 KB of
+// reads instead of once per 24 KB.  Measured on B200 (profiles/bench_r02_c_ab_*.json, 100-base reads): 240 reads
+// per tile 267.0 / 221.7 G lookups/s (128 MiB / 1 GiB table), 320: 266.8 / 226.2, 409 (a full pass): 277.5 / 234.3.
 #ifndef HAST_READS_PER_TILE
-#define HAST_READS_PER_TILE 240
+#define HAST_READS_PER_TILE 640
 #endif
 #ifndef HAST_FUSED_THREADS
 #define HAST_FUSED_THREADS 256
@@ -62,13 +67,22 @@ namespace hast {
 #define HAST_FUSED_CTAS_PER_SM 4
 #endif
 constexpr int kFusedThreads = HAST_FUSED_THREADS;        // threads per CTA of classify_kernel
-constexpr int kFusedReadsPerTile = HAST_READS_PER_TILE;
+constexpr int kFusedReadsPerTile = HAST_READS_PER_TILE;   // upper bound; see fused_reads_per_tile
 constexpr int kQueueCap = 768 * (HAST_FUSED_THREADS / 32);                          // passing positions buffered per CTA
 constexpr int kChunk = 16;                               // positions per thread per sweep (= bases per packed word)
 constexpr int kDrainUnroll = 4;                          // exact probes in flight per thread while draining
 constexpr int kWarpQueueCap = kQueueCap / (kFusedThreads / 32);             // every warp of the CTA queues and drains on its own
 constexpr uint32_t kDrainChunk = 32u * kDrainUnroll;     // one full round of probes for a warp
 static_assert(kWarpQueueCap >= (int)kDrainChunk - 1 + 16 * 32, "eight warps; a sweep appends up to 16 positions per lane");
+
+// reads per tile for a batch: what fills one pass (cap - 16 bytes) at the batch's mean read length
+__host__ __device__ inline uint32_t fused_reads_per_tile(uint64_t n_bases, uint32_t n_reads, uint32_t pass_cap) {
+    const uint64_t mean = n_reads ? (n_bases + n_reads - 1) / n_reads : 1;
+    uint64_t r = (pass_cap - 16u) / (mean ? mean : 1);
+    if (r > (uint64_t)kFusedReadsPerTile) r = kFusedReadsPerTile;
+    if (r < 32) r = 32;
+    return (uint32_t)r;
+}
 
 template <bool TMA>
 struct __align__(128) FusedSmem {
@@ -181,7 +195,7 @@ classify_kernel(TableView t, BatchView b, int32_t* __restrict__ counts, uint32_t
     using Smem = FusedSmem<TMA>;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     constexpr uint32_t kPassCapBytes = Smem::kCap;
-    constexpr uint32_t kReadsPerTile = kFusedReadsPerTile;
+    const uint32_t kReadsPerTile = b.reads_per_tile;       // <= kFusedReadsPerTile (set by the launcher)
     uint32_t* const s_off = sm.off;
     uint32_t* const s_votes = sm.votes;
     uint32_t* const s_packed = sm.packed;

@@ -118,6 +118,7 @@ struct hast_ctx {
                                           // mini_len(k) != 0 in table.cuh; every other k -- 17 included -- runs as 1), 4 = as 3 with TMA-staged reads,
                                           // 1 = classify_kernel (per-k-mer filter word), 2 = same with TMA-staged reads, 0 = tile_kernel<MODE_CLASSIFY>
     int64_t opt_seq_mode = 0;             // 1 = stage-03 window rule (classify_kernel<.., SEQ>)
+    int64_t opt_reads_per_tile = 0;       // 0 = per batch, what fills one pass (fused_reads_per_tile); else fixed (tuning / tests)
     int64_t opt_filter_bits_per_key = 16;
     int64_t opt_filter_max_bytes = (int64_t)64 << 20;
     // stage 00 (kcount.cuh)
@@ -169,13 +170,17 @@ int read_stats(hast_ctx* ctx, DevStats* out) {
     return HAST_OK;
 }
 
-int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv, uint64_t* d_kmers, uint8_t* d_has_n) {
+int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv_in, uint64_t* d_kmers, uint8_t* d_has_n) {
+    BatchView bv = bv_in;
     const uint32_t n_tiles = (bv.n_reads + kReadsPerTile - 1) / kReadsPerTile;
     if (!n_tiles) return HAST_OK;
     const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)ctx->tile_blocks);
     if (mode == MODE_CLASSIFY && ctx->opt_kernel >= 1) {
-        const uint32_t n_ftiles = (bv.n_reads + kFusedReadsPerTile - 1) / kFusedReadsPerTile;
         const bool tma = (ctx->opt_kernel == 2 || ctx->opt_kernel == 4) && !bv.packed;
+        bv.reads_per_tile = ctx->opt_reads_per_tile > 0
+            ? (uint32_t)std::min<int64_t>(ctx->opt_reads_per_tile, kFusedReadsPerTile)
+            : fused_reads_per_tile(bv.n_bases, bv.n_reads, tma ? FusedSmem<true>::kCap : FusedSmem<false>::kCap);
+        const uint32_t n_ftiles = (bv.n_reads + bv.reads_per_tile - 1) / bv.reads_per_tile;
         const int fgrid = (int)std::min<uint32_t>(n_ftiles, (uint32_t)(tma ? ctx->fused_blocks_tma : ctx->fused_blocks));
         const uint32_t nbc = (uint32_t)std::min<uint64_t>(ctx->n_barcodes, 0xFFFFFFFFull);
 #define HAST_LAUNCH_K(KT)                                                                                         \
@@ -347,6 +352,9 @@ int hast_set_option(hast_ctx* ctx, const char* name, int64_t value) {
         if (value && ctx->table_ready && ctx->tv.filt_m)
             return fail(ctx, HAST_E_STATE, "seq_mode: set before hast_table_begin (the pre-filter layout differs)");
         ctx->opt_seq_mode = value;
+    } else if (n == "reads_per_tile") {
+        if (value < 0 || value > kFusedReadsPerTile) return fail(ctx, HAST_E_ARG, "reads_per_tile: 0 (automatic) .. " + std::to_string(kFusedReadsPerTile));
+        ctx->opt_reads_per_tile = value;
     } else if (n == "filter_bits_per_key") {
         if (value < 1 || value > 64) return fail(ctx, HAST_E_ARG, "filter_bits_per_key: 1..64");
         ctx->opt_filter_bits_per_key = value;

@@ -43,6 +43,8 @@ struct BatchView {
     // first base in the top two bits, reads back to back; bit i of has_n = read i contains 'N'
     const uint32_t* packed;
     const uint32_t* has_n;
+    // reads per tile of classify_kernel (fused.cuh), chosen per batch so that a tile's reads fill one pass
+    uint32_t reads_per_tile = 0;
 };
 
 constexpr int kTileThreads = 256;
