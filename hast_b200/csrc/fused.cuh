@@ -57,8 +57,10 @@ namespace hast {
 // cost of a tile -- six CTA barriers, the stragglers each of them waits for -- is then paid once per 40 KB of
 // reads instead of once per 24 KB.  Measured on B200 (profiles/bench_r02_c_ab_*.json, 100-base reads): 240 reads
 // per tile 267.0 / 221.7 G lookups/s (128 MiB / 1 GiB table), 320: 266.8 / 226.2, 409 (a full pass): 277.5 / 234.3.
+// (r02_d, the same with the tile size chosen per batch: 276-279 / 245-249 with room for 640 reads and passes of 40-56 KB;
+// 416 keeps the shared-memory arrays as small as the fixed 409 did, which measured best on the 1 GiB table: 250.9.)
 #ifndef HAST_READS_PER_TILE
-#define HAST_READS_PER_TILE 640
+#define HAST_READS_PER_TILE 416
 #endif
 #ifndef HAST_FUSED_THREADS
 #define HAST_FUSED_THREADS 256

@@ -267,10 +267,10 @@ int run_classify(const Options& opt, RunStats& st) {
     }
     std::atomic<size_t> next_file{0};
     const int n_readers = (int)std::min<size_t>({streams.size(), (size_t)opt.threads, (size_t)8});
-    // threads per gzip stream (inflate_par.h)
-    // decoding one gzip stream on several threads costs ~2.5x the parser's CPU per byte: three
-    // quarters of the cores go to the decoders, shared by the files read side by side
-    int inflate_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() * 3u / 4u / (unsigned)std::max(1, n_readers)));
+    // threads per gzip stream (inflate_par.h: one replays, the others entropy-decode).  Measured on a 16-core box with
+    // two streams (profiles/r02_d_gz_threads.txt): 5 / 6 / 7 / 8 threads per stream -> 12.6 / 10.7 / 12.9 / 13.9 M pairs/s;
+    // the decoders may outnumber the cores -- they and the parsers sleep when their queues are empty
+    int inflate_threads = (int)std::max(2u, std::min(8u, std::thread::hardware_concurrency() / (unsigned)std::max(1, n_readers)));
     if (const char* e = getenv("HAST_INFLATE_THREADS")) inflate_threads = std::max(1, atoi(e));
     std::atomic<int> readers_left{n_readers};
     std::vector<std::thread> readers;
