@@ -696,12 +696,12 @@ def leg_cfg3(args, R):
     free_b, _ = torch.cuda.mem_get_info()
     per_pair = 2 * L + 8
     fit = int((free_b - (6 << 30)) // per_pair)
-    want = (P_total + world - 1) // world
-    P_rank = int(-R.max_over_ranks(-float(max(1, min(want, fit)))))     # the same slicing on every rank
+    from hast_b200 import dist as hd
+    want, _ = hd.strong_slices(P_total, world)
+    cap = int(-R.max_over_ranks(-float(max(1, min(want, fit)))))        # the same slicing on every rank
+    P_rank, P_total_used = hd.strong_slices(P_total, world, cap)
     reduced_to_fit = P_rank < want
-    P_total_used = min(P_total, P_rank * world)
-    lo_pair = rank * P_rank
-    n_pair = max(0, min(P_rank, P_total_used - lo_pair))
+    lo_pair, n_pair = hd.slice_of(rank, P_rank, P_total_used)
     C_pairs = SUB_BATCH_READS // 2
     bases = torch.empty((2 * n_pair, L), dtype=torch.uint8, device=dev)
     bc = torch.empty(2 * n_pair, dtype=torch.int32, device=dev)

@@ -22,6 +22,23 @@ def batch_bounds(n_reads: int, reads_per_batch: int) -> list[tuple[int, int]]:
     return [(lo, min(lo + reads_per_batch, n_reads)) for lo in range(0, n_reads, reads_per_batch)]
 
 
+def strong_slices(n_pairs: int, world: int, fit_per_rank: int | None = None) -> tuple[int, int]:
+    """Strong scaling (bench.py cfg3 leg): the pair index space [0, n_pairs) is cut into `world` contiguous slices of
+    `per_rank` pairs, rank r taking [r * per_rank, min((r + 1) * per_rank, used)).  `fit_per_rank` caps a slice at what
+    one GPU's HBM holds; every rank must call this with the SAME cap (bench.py takes the minimum over ranks).
+    -> (per_rank, used): used <= n_pairs is what the job classifies in total."""
+    per_rank = (n_pairs + world - 1) // world
+    if fit_per_rank is not None:
+        per_rank = max(1, min(per_rank, int(fit_per_rank)))
+    return per_rank, min(n_pairs, per_rank * world)
+
+
+def slice_of(rank: int, per_rank: int, used: int) -> tuple[int, int]:
+    """(first pair, number of pairs) of rank `rank` under strong_slices"""
+    lo = rank * per_rank
+    return lo, max(0, min(per_rank, used - lo))
+
+
 def reduce_counts(counts: np.ndarray, dst: int = 0):
     """Sum int32 counts[n_barcodes][2] over ranks to `dst` (BarcodeCache::Add, classify.cpp:57-63)."""
     import torch

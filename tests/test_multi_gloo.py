@@ -76,3 +76,69 @@ def test_shard_batches_partition():
         seen = sorted(i for r in range(world) for i in hd.shard_batches(37, r, world))
         assert seen == list(range(37))
     assert hd.batch_bounds(10, 4) == [(0, 4), (4, 8), (8, 10)]
+
+
+def _worker_strong(rank, world, port, out_dir):
+    """bench.py's cfg3 leg on CPU: every rank builds the same streamed trio, generates ITS contiguous slice of the pair
+    index space from (seed, pair index), classifies it (oracle standing in for the GPU), the partial counts are summed to
+    rank 0, and rank 0 checks a barcode-complete subsample of the REDUCED counts against the oracle on reads it
+    regenerates itself -- pairs that lie in both ranks' slices."""
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch.distributed as dist
+    import oracle as orc
+    from hast_b200 import dist as hd
+    from hast_b200 import synth_stream as ss
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    spec = ss.stream_config("stream_tiny")
+    spec.n_pairs = 3001                                    # not a multiple of the world size
+    t = ss.StreamTrio(spec, "cpu")
+    o = orc.Oracle()
+    o.load_kmers_packed(t.pat, spec.k, 0)
+    o.load_kmers_packed(t.mat, spec.k, 1)
+    o.init_adaptor()
+    per_rank, used = hd.strong_slices(spec.n_pairs, world)
+    lo, n = hd.slice_of(rank, per_rank, used)
+    bases, bc = t.gen_pairs(lo, n)
+    L = spec.read_len
+    off = np.arange(2 * n + 1, dtype=np.uint64) * np.uint64(L)
+    part, _ = o.classify_batch(bases.numpy().reshape(-1), off, bc.numpy().view(np.uint32), t.n_barcodes, nthreads=1)
+    local_sum = np.array([int(part[:, 0].sum()), int(part[:, 1].sum())], np.int64)     # before the reduce (in place on rank 0)
+    total = hd.reduce_counts(part, dst=0)
+    import torch
+    ls = torch.from_numpy(local_sum.copy())
+    dist.all_reduce(ls)
+    if rank == 0:
+        ids = np.arange(3, spec.n_barcodes, 7)
+        idx = t.pairs_of_barcodes(ids, 0, used)
+        sb, s_bc = t.gen_pairs_idx(idx)
+        s_off = np.arange(sb.shape[0] + 1, dtype=np.uint64) * np.uint64(L)
+        want, _ = o.classify_batch(sb.reshape(-1), s_off, s_bc, t.n_barcodes, nthreads=1)
+        by_rank = np.bincount(idx // per_rank, minlength=world)
+        np.save(Path(out_dir) / "strong.npy", np.array([
+            int((total[ids] == want[ids]).all()), int(want[ids].sum() > 0), int((by_rank > 0).all()),
+            int(ls.tolist() == [int(total[:, 0].sum()), int(total[:, 1].sum())]), int(used == spec.n_pairs)]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_strong_scaling_slices_and_subsample_parity(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_strong, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert np.load(tmp_path / "strong.npy").tolist() == [1, 1, 1, 1, 1]
+
+
+def test_strong_slices_cover_the_index_space():
+    from hast_b200 import dist as hd
+    for n, world in ((600_000_000, 8), (3001, 2), (7, 8), (100, 1)):
+        per, used = hd.strong_slices(n, world)
+        sl = [hd.slice_of(r, per, used) for r in range(world)]
+        assert used == n and sum(c for _, c in sl) == n
+        pos = 0
+        for lo, c in sl:
+            assert (lo == pos or c == 0) and c >= 0
+            pos += c
+    per, used = hd.strong_slices(600_000_000, 2, fit_per_rank=250_000_000)     # HBM holds less than a slice
+    assert (per, used) == (250_000_000, 500_000_000)
