@@ -129,45 +129,43 @@ int run_classify(const Options& opt, RunStats& st) {
 
     std::vector<hast_ctx*> ctx((size_t)n_gpu, nullptr);
     auto cleanup = [&] { for (hast_ctx* c : ctx) hast_destroy(c); };
-    for (int g = 0; g < n_gpu && !parse_only; ++g) {
-        if (hast_create(g, &ctx[(size_t)g]) != HAST_OK) {
-            fprintf(stderr, "ERROR : %s\n", hast_last_error(nullptr));
-            cleanup();
-            return 1;
-        }
-    }
-#define HCHECK(c, call)                                                     \
-    do {                                                                    \
-        if ((call) != HAST_OK) {                                            \
-            fprintf(stderr, "ERROR : %s\n", hast_last_error(c));            \
-            cleanup();                                                      \
-            return 1;                                                       \
-        }                                                                   \
-    } while (0)
 
     fprintf(stderr, "__START__\n use hap0 weight %g\n use hap1 weight %g\n", opt.weight0, opt.weight1);
     fprintf(stderr, " use %d GPU(s), %d parser thread(s)\n", n_gpu, opt.threads);
     logtime();
 
     // ---- k-mer table (load_kmers x2 + InitAdaptor, classify.cpp:433-437) -----------
-    if (!parse_only) {
+    // Built on its own thread -- CUDA start-up, the two list files, the inserts, the clones -- WHILE the readers and
+    // parsers below already fill batches: parsing needs no table, only the first kernel launch does.  The GPU threads
+    // wait for `table_ready`; a failure here aborts the pipeline like any other stage's.
+    std::mutex tb_mu;
+    std::condition_variable tb_cv;
+    bool table_ready = parse_only, table_failed = false;
+    std::string table_err;
+    auto build_table = [&]() -> std::string {
+#define TCHECK(c, call)                                                     \
+    do {                                                                    \
+        if ((call) != HAST_OK) return std::string(hast_last_error(c));      \
+    } while (0)
+        for (int g = 0; g < n_gpu; ++g)
+            if (hast_create(g, &ctx[(size_t)g]) != HAST_OK) return std::string(hast_last_error(nullptr));
         KmerList l0, l1;
         fprintf(stderr, "__load hap0 kmers__\n");
         std::string e = load_kmer_list(opt.hap0, 0, 0, l0);
-        if (!e.empty()) { fprintf(stderr, "ERROR : %s\n", e.c_str()); cleanup(); return 1; }
+        if (!e.empty()) return e;
         fprintf(stderr, "Recorded %llu haplotype 0 specific %d-mers\n", (unsigned long long)l0.n_lines, l0.k);
         fprintf(stderr, "__load hap1 kmers__\n");
         e = load_kmer_list(opt.hap1, 1, l0.k, l1);
-        if (!e.empty()) { fprintf(stderr, "ERROR : %s\n", e.c_str()); cleanup(); return 1; }
+        if (!e.empty()) return e;
         fprintf(stderr, "Recorded %llu haplotype 1 specific %d-mers\n", (unsigned long long)l1.n_lines, l0.k);
 
         uint64_t expected = l0.n_lines + l1.n_lines;
         for (int attempt = 0;; ++attempt) {
-            HCHECK(ctx[0], hast_table_begin(ctx[0], l0.k, expected));
+            TCHECK(ctx[0], hast_table_begin(ctx[0], l0.k, expected));
             int rc = hast_table_add_text(ctx[0], l0.text.data(), l0.n_lines, 0);
             if (rc == HAST_OK) rc = hast_table_add_text(ctx[0], l1.text.data(), l1.n_lines, 1);
             if (rc == HAST_E_TABLE_FULL && attempt < 4) { expected = expected * 2 + 64; continue; }
-            if (rc != HAST_OK) { fprintf(stderr, "ERROR : %s\n", hast_last_error(ctx[0])); cleanup(); return 1; }
+            if (rc != HAST_OK) return std::string(hast_last_error(ctx[0]));
             break;
         }
         fprintf(stderr, "Adaptor forward :%s\nAdaptor reverse :%s\n", opt.adaptor_f.c_str(), opt.adaptor_r.c_str());
@@ -175,7 +173,7 @@ int run_classify(const Options& opt, RunStats& st) {
             std::vector<uint64_t> er(ad->size() + 1);
             std::vector<uint8_t> tg(ad->size() + 1);
             uint32_t n = 0;
-            HCHECK(ctx[0], hast_table_erase_seq(ctx[0], ad->data(), (uint32_t)ad->size(), er.data(), tg.data(),
+            TCHECK(ctx[0], hast_table_erase_seq(ctx[0], ad->data(), (uint32_t)ad->size(), er.data(), tg.data(),
                                                 (uint32_t)er.size(), &n));
             for (uint32_t i = 0; i < n && i < er.size(); ++i)       // classify.cpp:319-337
                 for (int h = 0; h < 2; ++h)
@@ -184,18 +182,20 @@ int run_classify(const Options& opt, RunStats& st) {
                                 kmer_to_string(er[i], l0.k).c_str());
         }
         hast_table_info ti;
-        HCHECK(ctx[0], hast_table_info_get(ctx[0], &ti));
+        TCHECK(ctx[0], hast_table_info_get(ctx[0], &ti));
         st.size0 = ti.size[0];
         st.size1 = ti.size[1];
         st.table_bytes = ti.bytes;
         fprintf(stderr, " table : %llu buckets (%.1f MiB), %llu distinct k-mers, %llu displaced, |S0|=%llu |S1|=%llu\n",
                 (unsigned long long)ti.n_buckets, ti.bytes / 1048576.0, (unsigned long long)ti.n_entries,
                 (unsigned long long)ti.n_displaced, (unsigned long long)ti.size[0], (unsigned long long)ti.size[1]);
-        for (int g = 1; g < n_gpu; ++g) HCHECK(ctx[(size_t)g], hast_table_clone(ctx[(size_t)g], ctx[0]));
-    }
-    if (n_gpu > 1 && !parse_only) HCHECK(ctx[0], hast_comm_init_all(ctx.data(), n_gpu));
-    st.t_table = now() - t_start;
-    logtime();
+        for (int g = 1; g < n_gpu; ++g) TCHECK(ctx[(size_t)g], hast_table_clone(ctx[(size_t)g], ctx[0]));
+        if (n_gpu > 1) TCHECK(ctx[0], hast_comm_init_all(ctx.data(), n_gpu));
+#undef TCHECK
+        st.t_table = now() - t_start;
+        logtime();
+        return "";
+    };
 
     // ---- streaming classification ---------------------------------------------------
     const double t_reads0 = now();
@@ -265,6 +265,20 @@ int run_classify(const Options& opt, RunStats& st) {
         }
         streams.push_back(path);
     }
+    std::thread table_thread;
+    if (!parse_only)
+        table_thread = std::thread([&] {
+            const std::string e = build_table();
+            {
+                std::lock_guard<std::mutex> lk(tb_mu);
+                if (e.empty()) table_ready = true;
+                else { table_failed = true; table_err = e; }
+            }
+            if (!e.empty()) { sh.fail(e); abort_all(); }
+            tb_cv.notify_all();
+        });
+    // join before any early return below destroys what the thread uses
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } table_joiner{table_thread};
     std::atomic<size_t> next_file{0};
     const int n_readers = (int)std::min<size_t>({streams.size(), (size_t)opt.threads, (size_t)8});
     // threads per gzip stream (inflate_par.h: one replays, the others entropy-decode).  Measured on a 16-core box with
@@ -349,7 +363,6 @@ int run_classify(const Options& opt, RunStats& st) {
     std::vector<std::thread> gpu_threads;
     for (int g = 0; g < n_gpu; ++g)
         gpu_threads.emplace_back([&, g] {
-            hast_ctx* c = ctx[(size_t)g];
             uint64_t reserved = 0;
             std::deque<std::pair<uint64_t, Batch*>> inflight;
             Batch* b = nullptr;
@@ -365,6 +378,12 @@ int run_classify(const Options& opt, RunStats& st) {
                 q_batch_free.push(b);
             }
             if (parse_only) return;
+            {                                                  // parsing runs ahead; the first launch needs the table
+                std::unique_lock<std::mutex> lk(tb_mu);
+                tb_cv.wait(lk, [&] { return table_ready || table_failed; });
+                if (table_failed) return;
+            }
+            hast_ctx* c = ctx[(size_t)g];
             while (q_batch.pop(b)) {
                 const uint64_t need = (uint64_t)b->max_barcode + 1;
                 if (need > reserved) {
@@ -394,6 +413,7 @@ int run_classify(const Options& opt, RunStats& st) {
     for (auto& t : readers) t.join();
     for (auto& t : parsers) t.join();
     for (auto& t : gpu_threads) t.join();
+    if (table_thread.joinable()) table_thread.join();
     if (sh.failed) {
         fprintf(stderr, "ERROR : %s\n", sh.error.c_str());
         free_batches(); cleanup();
