@@ -440,6 +440,8 @@ def leg_cfg2(args, R):
         eng.set_option("l2_fetch_granularity", args.l2_fetch)
     if args.reads_per_tile:
         eng.set_option("reads_per_tile", args.reads_per_tile)
+    if args.l2_persist_mib >= 0:
+        eng.set_option("l2_persist_bytes", args.l2_persist_mib << 20)
     info, t_table = build_table(eng, spec.k, trio.pat, trio.mat, args.table_scale)
     log(f"rank {rank}: table {info.bytes / 2**20:.0f} MiB + pre-filter {info.filter_bytes / 2**20:.1f} MiB, {info.n_entries} entries, "
         f"{info.n_overflow_buckets} overflow buckets, {info.n_displaced} displaced, built in {t_table:.2f}s")
@@ -686,6 +688,8 @@ def leg_cfg3(args, R):
     eng.set_option("filter_max_bytes", args.filter_max_mib << 20)
     if args.reads_per_tile:
         eng.set_option("reads_per_tile", args.reads_per_tile)
+    if args.l2_persist_mib >= 0:
+        eng.set_option("l2_persist_bytes", args.l2_persist_mib << 20)
     info, t_table = build_table(eng, spec.k, trio.pat, trio.mat)
     eng.reserve_barcodes(nb)
     R.comm_for(eng)
@@ -889,6 +893,7 @@ def main():
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (32/64/128), 0 = leave")
     ap.add_argument("--filter-max-mib", type=int, default=64, help="pre-filter size cap (MiB)")
     ap.add_argument("--reads-per-tile", type=int, default=0, help="fused kernel: reads per tile (0 = what fills one pass)")
+    ap.add_argument("--l2-persist-mib", type=int, default=-1, help="tuning: L2 set-aside for persisting accesses (MiB); -1 = leave")
     ap.add_argument("--only-cfg3", action="store_true", help="tuning: run the cfg3 leg alone and print its object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "hast_b200" else args.warmup

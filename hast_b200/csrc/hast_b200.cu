@@ -118,6 +118,7 @@ struct hast_ctx {
                                           // mini_len(k) != 0 in table.cuh; every other k -- 17 included -- runs as 1), 4 = as 3 with TMA-staged reads,
                                           // 1 = classify_kernel (per-k-mer filter word), 2 = same with TMA-staged reads, 0 = tile_kernel<MODE_CLASSIFY>
     int64_t opt_seq_mode = 0;             // 1 = stage-03 window rule (classify_kernel<.., SEQ>)
+    size_t l2_persist = 0;                // bytes of L2 set aside for persisting accesses (option l2_persist_bytes)
     int64_t opt_reads_per_tile = 0;       // 0 = per batch, what fills one pass (fused_reads_per_tile); else fixed (tuning / tests)
     int64_t opt_filter_bits_per_key = 16;
     int64_t opt_filter_max_bytes = (int64_t)64 << 20;
@@ -367,6 +368,17 @@ int hast_set_option(hast_ctx* ctx, const char* name, int64_t value) {
         if (value != 32 && value != 64 && value != 128) return fail(ctx, HAST_E_ARG, "l2_fetch_granularity: 32, 64 or 128");
         CU(cudaSetDevice(ctx->device));
         CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+    } else if (n == "l2_persist_bytes") {
+        // device-wide: L2 set aside for persisting accesses (cudaLimitPersistingL2CacheSize).  The pre-filter words are
+        // loaded with an L2 evict_last policy; without a set-aside the hardware has nowhere to keep them apart from the
+        // table sectors and read bytes that stream through.  Clamped to what the device allows; 0 = none.
+        if (value < 0) return fail(ctx, HAST_E_ARG, "l2_persist_bytes: >= 0");
+        CU(cudaSetDevice(ctx->device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, ctx->device));
+        const size_t want = std::min<size_t>((size_t)value, (size_t)prop.persistingL2CacheMaxSize);
+        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+        ctx->l2_persist = want;
     } else {
         return fail(ctx, HAST_E_ARG, "unknown option: " + n);
     }

@@ -72,7 +72,7 @@ def _run(e, job, sub, order=None):
 def test_full_size_properties(job):
     torch = job["torch"]
     t, L, n = job["t"], job["L"], job["n"]
-    e = _engine(1, t)
+    e = _engine(3, t)                              # the default kernel (minimizer-addressed pre-filter), as benchmarked
     whole, lookups = _run(e, job, 4_000_000)
     assert whole.sum() > 1_000_000 and lookups > 3_000_000_000
     # linearity under a different, ragged split
@@ -85,6 +85,12 @@ def test_full_size_properties(job):
     shuffled, lookups3 = _run(e, job, 4_000_000, order=perm)
     assert (shuffled == whole).all() and lookups3 == lookups
     e.close()
+    # the per-k-mer filter word (kernel 1) and a fixed small tile must agree with it
+    e1 = _engine(1, t)
+    e1.set_option("reads_per_tile", 100)
+    k1, lookups1 = _run(e1, job, 4_000_000)
+    assert (k1 == whole).all() and lookups1 == lookups
+    e1.close()
     # the direct-probe kernel walks the table differently and must agree
     e0 = _engine(0, t)
     direct, lookups4 = _run(e0, job, 4_000_000)
