@@ -117,6 +117,24 @@ def test_fused_parity(engine, k):
     assert (got3 == want).all()
 
 
+@pytest.mark.parametrize("k", [16, 21, 31])
+def test_tile_size_does_not_change_counts(engine, k):
+    """The tile size is chosen per batch so that a tile's reads fill one pass (fused_reads_per_tile); any fixed size --
+    one read per tile's worth of threads, an odd size, the largest -- and the automatic choice give the oracle's counts."""
+    case = cases.adversarial_case(k, 3000, seed=900 + k)
+    build_table(engine, case)
+    o, _ = build_oracle(case)
+    bases, off = cases.flatten(case["reads"])
+    want, lookups = o.classify_batch(bases, off, case["bc_ids"], len(case["bc_names"]))
+    try:
+        for rpt in (1, 33, 240, 416, 0):
+            engine.set_option("reads_per_tile", rpt)
+            got, st = run_fused(engine, case)
+            assert (got == want).all() and st["lookups"] == lookups, rpt
+    finally:
+        engine.set_option("reads_per_tile", 0)
+
+
 @pytest.mark.parametrize("k", [5, 17, 21, 32])
 def test_packed_batches_equal_ascii_batches(engine, k, request):
     """hast_submit_batch_packed (2-bit words + containN bits made on the host) == hast_submit_batch."""
