@@ -118,7 +118,7 @@ struct hast_ctx {
                                           // mini_len(k) != 0 in table.cuh; every other k -- 17 included -- runs as 1), 4 = as 3 with TMA-staged reads,
                                           // 1 = classify_kernel (per-k-mer filter word), 2 = same with TMA-staged reads, 0 = tile_kernel<MODE_CLASSIFY>
     int64_t opt_seq_mode = 0;             // 1 = stage-03 window rule (classify_kernel<.., SEQ>)
-    size_t l2_persist = 0;                // bytes of L2 set aside for persisting accesses (option l2_persist_bytes)
+    int64_t l2_persist = -1;              // bytes of L2 set aside for persisting accesses (option l2_persist_bytes); -1 = default
     int64_t opt_reads_per_tile = 0;       // 0 = per batch, what fills one pass (fused_reads_per_tile); else fixed (tuning / tests)
     int64_t opt_filter_bits_per_key = 16;
     int64_t opt_filter_max_bytes = (int64_t)64 << 20;
@@ -378,7 +378,7 @@ int hast_set_option(hast_ctx* ctx, const char* name, int64_t value) {
         CU(cudaGetDeviceProperties(&prop, ctx->device));
         const size_t want = std::min<size_t>((size_t)value, (size_t)prop.persistingL2CacheMaxSize);
         CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-        ctx->l2_persist = want;
+        ctx->l2_persist = (int64_t)want;
     } else {
         return fail(ctx, HAST_E_ARG, "unknown option: " + n);
     }
@@ -432,6 +432,16 @@ int hast_table_begin(hast_ctx* ctx, int k, uint64_t expected_keys) {
     CU(cudaMalloc(&ctx->tv.filt, ctx->filt_words * 8));
     CU(cudaMemsetAsync(ctx->tv.filt, 0, ctx->filt_words * 8, ctx->cs));
     ctx->tv.filt_shift = 32 - fb;
+    // The filter words are loaded with an L2 evict_last policy (fused.cuh).  That only has teeth when part of L2 is set
+    // aside for persisting accesses: with 64 MiB set aside the 64 MiB filter of a human-scale table keeps its place next
+    // to 1 GiB of table sectors and 160 MB of counters (B200, profiles/r02_f_l2_persist.txt: 250.1 -> 262.0 G lookups/s;
+    // the 16 MiB filter of a 128 MiB table fits L2 anyway: 276.8 -> 276.7).  Device-wide limit; the option overrides it.
+    if (ctx->l2_persist < 0) {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, ctx->device));
+        const size_t want = std::min<size_t>((size_t)64 << 20, (size_t)prop.persistingL2CacheMaxSize);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
+    }
     // minimizer-addressed filter for the k with a MINI sweep (fused.cuh; kernel 3 and its TMA-staged form 4);
     // the stage-03 window rule, kernels 1/2 and every other k use the per-k-mer filter word
     ctx->tv.filt_m = (ctx->opt_kernel >= 3 && !ctx->opt_seq_mode) ? (uint32_t)mini_len(k) : 0u;
