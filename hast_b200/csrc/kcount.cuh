@@ -15,9 +15,9 @@
 // so what the dump kernels emit is exactly the text jellyfish prints.
 //
 // Layout in HBM: 2^b slots of 16 bytes { key + 1 (0 = empty), count[paternal], count[maternal] },
-// linear probing from the start of a 128-byte LINE (8 slots) that is chosen by the k-mer's MINIMIZER
-// -- the smallest hash among the canonical m-mers inside it, the same for both strands -- not by the
-// k-mer itself.  Consecutive windows of a read share their minimizer for (k - m + 2) / 2 positions on
+// probed first in the 128-byte LINE (8 slots) chosen by the k-mer's MINIMIZER -- the smallest hash among
+// the canonical m-mers inside it, the same for both strands -- and only when that line is full by linear
+// probing from a hash of the k-mer itself (kc_insert).  Consecutive windows of a read share their minimizer for (k - m + 2) / 2 positions on
 // average, so their slots sit in the same line: the first of them pays the HBM miss, the others hit
 // L2.  (With the start chosen by a hash of the k-mer every window was an L2 miss on a random slot:
 // 96 B read + 29 B written per window against 16 B of slot, profiles/r01_f_kc_count_kernel.txt.)
@@ -75,10 +75,30 @@ __host__ __device__ __forceinline__ uint32_t recode32(uint32_t w) { return w ^ (
 __host__ __device__ __forceinline__ uint64_t recode64(uint64_t w) { return w ^ ((w >> 1) & 0x5555555555555555ull); }
 
 #ifdef __CUDACC__
+// Insert-or-increment.  Probe order: the 8 slots of the minimizer's line, then -- only when that line is full of
+// other keys -- ordinary linear probing from a hash of the k-mer itself.  Nothing is ever deleted, so "the home line
+// is full" is permanent and a key lives in its home line iff the line had room when it first arrived.  That is the
+// common case for the k-mers that matter: genomic k-mers occur ~coverage times and arrive early, the error k-mers
+// that would crowd a line (three quarters of the distinct keys at 30x) mostly arrive after it is full and go to
+// the overflow sequence, which costs them one random slot like before.
 __device__ __forceinline__ void kc_insert(const KcView& t, uint64_t canon, uint64_t mix, uint32_t parent,
                                           uint32_t& full) {
     const unsigned long long key = canon + 1ull;
-    uint64_t s = (mix << 3) & t.mask;                   // first slot of the minimizer's line
+    const uint64_t line = (mix << 3) & t.mask;          // first slot of the minimizer's line
+#pragma unroll 1
+    for (uint32_t i = 0; i < 8u; ++i) {
+        KcSlot* slot = t.slots + ((line + i) & t.mask);
+        unsigned long long cur = *(volatile unsigned long long*)&slot->key;
+        if (cur == 0ull) {
+            cur = atomicCAS(&slot->key, 0ull, key);
+            if (cur == 0ull) cur = key;
+        }
+        if (cur == key) {
+            atomicAdd(&slot->cnt[parent], 1u);
+            return;
+        }
+    }
+    uint64_t s = kc_mix(canon) & t.mask;
     for (uint32_t probe = 0; probe < t.max_probe; ++probe) {
         KcSlot* slot = t.slots + s;
         unsigned long long cur = *(volatile unsigned long long*)&slot->key;

@@ -37,7 +37,6 @@ std::string PlainSlicer::open(const std::string& path, size_t slice_bytes) {
     n_slices_ = (size_ + slice_ - 1) / slice_;
     hand_.reset(new Hand[n_slices_ + 1]);
     hand_[0].ready.store(1, std::memory_order_release);
-    if (getenv("HAST_NO_POPULATE")) populate_ = false;
     return "";
 }
 
@@ -57,13 +56,6 @@ bool PlainSlicer::next(TextBlock& blk, bool* first, uint64_t* index) {
 #ifdef MADV_WILLNEED
     if (i + 2 < n_slices_) madvise(const_cast<char*>(map_ + a + 2 * slice_), (size_t)std::min(slice_, size_ - a - 2 * slice_), MADV_WILLNEED);
 #endif
-    // map the slice's pages in one call instead of one fault per 16 pages while the index pass walks them
-    // (MADV_POPULATE_READ, Linux 5.14+; an older kernel answers EINVAL and the pass faults them in as before)
-    if (populate_) {
-        const uintptr_t pa = reinterpret_cast<uintptr_t>(buf) & ~(uintptr_t)4095;
-        const size_t plen = (size_t)(reinterpret_cast<uintptr_t>(buf) + n - pa);
-        if (madvise(reinterpret_cast<void*>(pa), plen, 22 /* MADV_POPULATE_READ */) != 0) populate_ = false;
-    }
     constexpr size_t kFront = 8;                    // index slots kept free for the newlines of a straddling record
     const uint64_t c = newline_index(buf, n, blk.nl, kFront);
     uint32_t* nl = blk.nl.data() + kFront;

@@ -47,7 +47,6 @@ private:
     const char* map_ = nullptr;
     uint64_t size_ = 0, slice_ = 0, n_slices_ = kNotRegular;
     std::atomic<uint64_t> next_{0};
-    std::atomic<bool> populate_{true};
     std::unique_ptr<Hand[]> hand_;
 };
 
