@@ -76,41 +76,50 @@ __host__ __device__ __forceinline__ uint64_t recode64(uint64_t w) { return w ^ (
 
 #ifdef __CUDACC__
 // Insert-or-increment.  Probe order: the 8 slots of the minimizer's line, then -- only when that line is full of
-// other keys -- ordinary linear probing from a hash of the k-mer itself.  Nothing is ever deleted, so "the home line
+// other keys -- open addressing from a hash of the k-mer itself.  Nothing is ever deleted, so "the home line
 // is full" is permanent and a key lives in its home line iff the line had room when it first arrived.  That is the
 // common case for the k-mers that matter: genomic k-mers occur ~coverage times and arrive early, the error k-mers
 // that would crowd a line (three quarters of the distinct keys at 30x) mostly arrive after it is full and go to
 // the overflow sequence, which costs them one random slot like before.
+__device__ __forceinline__ bool kc_try_slot(KcSlot* slot, unsigned long long key, uint32_t parent) {
+    unsigned long long cur = *(volatile unsigned long long*)&slot->key;
+    if (cur == 0ull) {
+        cur = atomicCAS(&slot->key, 0ull, key);
+        if (cur == 0ull) cur = key;
+    }
+    if (cur != key) return false;
+    atomicAdd(&slot->cnt[parent], 1u);
+    return true;
+}
+
 __device__ __forceinline__ void kc_insert(const KcView& t, uint64_t canon, uint64_t mix, uint32_t parent,
                                           uint32_t& full) {
     const unsigned long long key = canon + 1ull;
     const uint64_t line = (mix << 3) & t.mask;          // first slot of the minimizer's line
-#pragma unroll 1
-    for (uint32_t i = 0; i < 8u; ++i) {
-        KcSlot* slot = t.slots + ((line + i) & t.mask);
-        unsigned long long cur = *(volatile unsigned long long*)&slot->key;
-        if (cur == 0ull) {
-            cur = atomicCAS(&slot->key, 0ull, key);
-            if (cur == 0ull) cur = key;
-        }
-        if (cur == key) {
-            atomicAdd(&slot->cnt[parent], 1u);
-            return;
-        }
+    // the eight keys of the home line, all loads in flight at once (one L2 / HBM round trip, no divergence)
+    unsigned long long kk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) kk[i] = *(volatile unsigned long long*)&t.slots[(line + (uint64_t)i) & t.mask].key;
+    uint32_t hit = 8u, empty = 8u;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (kk[i] == key) hit = (uint32_t)i;
+        if (kk[i] == 0ull) empty = (uint32_t)i;
     }
+    if (hit < 8u) {                                     // seen before: the common case
+        atomicAdd(&t.slots[(line + hit) & t.mask].cnt[parent], 1u);
+        return;
+    }
+    // slots before the first empty one held other keys and never change; from there on look again, slot by slot
+    // (somebody may have put this very key there since the loads above)
+    for (uint32_t i = empty; i < 8u; ++i)
+        if (kc_try_slot(t.slots + ((line + i) & t.mask), key, parent)) return;
+    // the home line is full of other keys: overflow sequence from a hash of the k-mer, one slot per line (stride 9 is
+    // odd, so the sequence visits every slot, and it does not walk through the full lines the table is made of)
     uint64_t s = kc_mix(canon) & t.mask;
     for (uint32_t probe = 0; probe < t.max_probe; ++probe) {
-        KcSlot* slot = t.slots + s;
-        unsigned long long cur = *(volatile unsigned long long*)&slot->key;
-        if (cur == 0ull) {
-            cur = atomicCAS(&slot->key, 0ull, key);
-            if (cur == 0ull) cur = key;
-        }
-        if (cur == key) {
-            atomicAdd(&slot->cnt[parent], 1u);
-            return;
-        }
-        s = (s + 1) & t.mask;
+        if (kc_try_slot(t.slots + s, key, parent)) return;
+        s = (s + 9ull) & t.mask;
     }
     ++full;
 }
