@@ -245,10 +245,14 @@ kc_count_kernel(KcView t, BatchView b, uint32_t parent, KcStats* __restrict__ st
                 set_bits(s_bad, hi - lo, nseg * 16u);
             }
             __syncthreads();
-            // (c)
-            for (uint32_t wi = tid; wi < nseg; wi += kTileThreads) {
-                uint32_t valid = ~(s_bad[wi >> 1] >> ((wi & 1u) * 16u)) & 0xFFFFu;
-                if (!valid) continue;
+            // (c)  The loop bound is warp-uniform and every position ends in __syncwarp(): the probe loops of
+            // kc_insert diverge, and without a barrier the lanes of a warp stayed apart for the rest of their 16
+            // positions -- capture r02_i showed the whole sweep running with ONE active thread per warp.
+            for (uint32_t wbase = 0; wbase < nseg; wbase += kTileThreads) {
+                const uint32_t wi = min(wbase + tid, nseg - 1u);
+                uint32_t valid = 0;
+                if (wbase + tid < nseg) valid = ~(s_bad[wi >> 1] >> ((wi & 1u) * 16u)) & 0xFFFFu;
+                if (!__any_sync(0xFFFFFFFFu, valid != 0u)) continue;
                 st_windows += __popc(valid);
                 const uint32_t w0 = s_packed[wi], w1 = s_packed[wi + 1];
                 const uint32_t nxt = __funnelshift_l(s_packed[wi + nxt_word + 1], s_packed[wi + nxt_word], nxt_sh);
@@ -276,7 +280,7 @@ kc_count_kernel(KcView t, BatchView b, uint32_t parent, KcStats* __restrict__ st
                         hq[0] = kc_hash_m(fm < rm ? fm : rm);
                     }
                 }
-#pragma unroll 4
+#pragma unroll 2
                 for (int j = 0; j < 16; ++j) {
                     const uint32_t c = (nxt >> (30 - 2 * j)) & 3u;
                     fwd = ((fwd << 2) | c) & kmask;
@@ -286,17 +290,17 @@ kc_count_kernel(KcView t, BatchView b, uint32_t parent, KcStats* __restrict__ st
 #pragma unroll
                     for (int q = 7; q > 0; --q) hq[q] = hq[q - 1];
                     hq[0] = kc_hash_m(fm < rm ? fm : rm);
-                    if ((valid >> j) & 1u) {
-                        const uint64_t canon = fwd < rcv ? fwd : rcv;
-                        uint32_t hmin = hq[0];         // the k-mer's mw m-mers are the newest mw entries
+                    const uint64_t canon = fwd < rcv ? fwd : rcv;
+                    uint32_t hmin = hq[0];             // the k-mer's mw m-mers are the newest mw entries
 #pragma unroll
-                        for (int q = 1; q < 8; ++q) hmin = min(hmin, hq[q] | keep[q]);
-                        const uint64_t mix = kc_mix_mini(hmin);
-                        if (t.n_parts == 1u || kc_part_of(mix, t.n_parts) == t.part) {
-                            ++st_counted;
-                            kc_insert(t, canon, mix, parent, st_full);
-                        }
+                    for (int q = 1; q < 8; ++q) hmin = min(hmin, hq[q] | keep[q]);
+                    const uint64_t mix = kc_mix_mini(hmin);
+                    const bool mine = ((valid >> j) & 1u) && (t.n_parts == 1u || kc_part_of(mix, t.n_parts) == t.part);
+                    if (mine) {
+                        ++st_counted;
+                        kc_insert(t, canon, mix, parent, st_full);
                     }
+                    __syncwarp();
                 }
             }
             ra = rb;
