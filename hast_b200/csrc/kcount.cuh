@@ -15,17 +15,11 @@
 // so what the dump kernels emit is exactly the text jellyfish prints.
 //
 // Layout in HBM: 2^b slots of 16 bytes { key + 1 (0 = empty), count[paternal], count[maternal] },
-// probed first in the 128-byte LINE (8 slots) chosen by the k-mer's MINIMIZER -- the smallest hash among
-// the canonical m-mers inside it, the same for both strands -- and only when that line is full by linear
-// probing from a hash of the k-mer itself (kc_insert).  Consecutive windows of a read share their minimizer for (k - m + 2) / 2 positions on
-// average, so their slots sit in the same line: the first of them pays the HBM miss, the others hit
-// L2.  (With the start chosen by a hash of the k-mer every window was an L2 miss on a random slot:
-// 96 B read + 29 B written per window against 16 B of slot, profiles/r01_f_kc_count_kernel.txt.)
-// m = 14 for k = 17..21, k - 7 above (eight m-mers per k-mer); k <= 16 keeps one k-mer per start.
-// A context may own just one PARTITION of the key space (the top bits of the same minimizer hash):
-// a table for both human parents (several 10^9 distinct k-mers with their error k-mers) does not fit
-// one GPU, so the reads are streamed once per partition, or once to several GPUs that each keep a
-// different one.  Bound by 16-byte atomics in L2 / HBM; no tensor cores.
+// linear probing from the low bits of a 64-bit mix of the key.  A context may own just one
+// PARTITION of the key space (the top bits of the same mix): a table for both human parents
+// (several 10^9 distinct k-mers with their error k-mers) does not fit one GPU, so the reads
+// are streamed once per partition, or once to several GPUs that each keep a different one.
+// Bound by random 16-byte atomics on HBM; no tensor cores.
 #pragma once
 #include <cstdint>
 #include "kernels.cuh"
@@ -59,15 +53,6 @@ __host__ __device__ __forceinline__ uint64_t kc_mix(uint64_t x) {      // murmur
 __host__ __device__ __forceinline__ uint32_t kc_part_of(uint64_t mix, uint32_t n_parts) {
     return (uint32_t)(((mix >> 32) * (uint64_t)n_parts) >> 32);
 }
-// minimizer geometry: m-mers per k-mer and their length
-__host__ __device__ __forceinline__ int kc_mini_count(int k) { return k >= 17 ? (k - 13 < 8 ? k - 13 : 8) : 1; }
-__host__ __device__ __forceinline__ uint32_t kc_hash_m(uint64_t cm) {       // canonical m-mer -> 32 bits
-    uint32_t h = ((uint32_t)cm ^ ((uint32_t)(cm >> 32) * 0x9E3779B1u)) * 0x85EBCA6Bu;
-    h ^= h >> 15; h *= 0xC2B2AE35u; h ^= h >> 16;
-    return h;
-}
-// the minimum of several hashes is biased towards small values: mix again before it picks a line / a partition
-__host__ __device__ __forceinline__ uint64_t kc_mix_mini(uint32_t hmin) { return kc_mix((uint64_t)hmin * 0x9E3779B97F4A7C15ull); }
 
 // kmer.h-coded 2-bit fields (A0 C1 T2 G3, what pack16 produces) <-> jellyfish code (A0 C1 G2 T3):
 // x ^ (x >> 1) per field, an involution on {0,1,2,3} that swaps 2 and 3
@@ -75,51 +60,22 @@ __host__ __device__ __forceinline__ uint32_t recode32(uint32_t w) { return w ^ (
 __host__ __device__ __forceinline__ uint64_t recode64(uint64_t w) { return w ^ ((w >> 1) & 0x5555555555555555ull); }
 
 #ifdef __CUDACC__
-// Insert-or-increment.  Probe order: the 8 slots of the minimizer's line, then -- only when that line is full of
-// other keys -- open addressing from a hash of the k-mer itself.  Nothing is ever deleted, so "the home line
-// is full" is permanent and a key lives in its home line iff the line had room when it first arrived.  That is the
-// common case for the k-mers that matter: genomic k-mers occur ~coverage times and arrive early, the error k-mers
-// that would crowd a line (three quarters of the distinct keys at 30x) mostly arrive after it is full and go to
-// the overflow sequence, which costs them one random slot like before.
-__device__ __forceinline__ bool kc_try_slot(KcSlot* slot, unsigned long long key, uint32_t parent) {
-    unsigned long long cur = *(volatile unsigned long long*)&slot->key;
-    if (cur == 0ull) {
-        cur = atomicCAS(&slot->key, 0ull, key);
-        if (cur == 0ull) cur = key;
-    }
-    if (cur != key) return false;
-    atomicAdd(&slot->cnt[parent], 1u);
-    return true;
-}
-
 __device__ __forceinline__ void kc_insert(const KcView& t, uint64_t canon, uint64_t mix, uint32_t parent,
                                           uint32_t& full) {
     const unsigned long long key = canon + 1ull;
-    const uint64_t line = (mix << 3) & t.mask;          // first slot of the minimizer's line
-    // the eight keys of the home line, all loads in flight at once (one L2 / HBM round trip, no divergence)
-    unsigned long long kk[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) kk[i] = *(volatile unsigned long long*)&t.slots[(line + (uint64_t)i) & t.mask].key;
-    uint32_t hit = 8u, empty = 8u;
-#pragma unroll
-    for (int i = 7; i >= 0; --i) {
-        if (kk[i] == key) hit = (uint32_t)i;
-        if (kk[i] == 0ull) empty = (uint32_t)i;
-    }
-    if (hit < 8u) {                                     // seen before: the common case
-        atomicAdd(&t.slots[(line + hit) & t.mask].cnt[parent], 1u);
-        return;
-    }
-    // slots before the first empty one held other keys and never change; from there on look again, slot by slot
-    // (somebody may have put this very key there since the loads above)
-    for (uint32_t i = empty; i < 8u; ++i)
-        if (kc_try_slot(t.slots + ((line + i) & t.mask), key, parent)) return;
-    // the home line is full of other keys: overflow sequence from a hash of the k-mer, one slot per line (stride 9 is
-    // odd, so the sequence visits every slot, and it does not walk through the full lines the table is made of)
-    uint64_t s = kc_mix(canon) & t.mask;
+    uint64_t s = mix & t.mask;
     for (uint32_t probe = 0; probe < t.max_probe; ++probe) {
-        if (kc_try_slot(t.slots + s, key, parent)) return;
-        s = (s + 9ull) & t.mask;
+        KcSlot* slot = t.slots + s;
+        unsigned long long cur = *(volatile unsigned long long*)&slot->key;
+        if (cur == 0ull) {
+            cur = atomicCAS(&slot->key, 0ull, key);
+            if (cur == 0ull) cur = key;
+        }
+        if (cur == key) {
+            atomicAdd(&slot->cnt[parent], 1u);
+            return;
+        }
+        s = (s + 1) & t.mask;
     }
     ++full;
 }
@@ -156,14 +112,6 @@ kc_count_kernel(KcView t, BatchView b, uint32_t parent, KcStats* __restrict__ st
     const uint32_t fwd_init_shift = 64u - 2u * (uint32_t)km1;
     const uint32_t rc_shift = 2u * (uint32_t)km1;
     const uint32_t nxt_word = (uint32_t)km1 >> 4, nxt_sh = ((uint32_t)km1 & 15u) * 2u;
-    // minimizer: mw canonical m-mers of mm bases per k-mer (kc_mini_count); entries of the hash ring older than mw
-    // are masked out of the minimum
-    const int mw = kc_mini_count(k), mm = k - mw + 1, mm1 = mm - 1;
-    const uint64_t mmask = kmer_mask(mm), mask_mm1 = kmer_mask(mm1);
-    const uint32_t rm_shift = 2u * (uint32_t)mm1;
-    uint32_t keep[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) keep[q] = q < mw ? 0u : 0xFFFFFFFFu;
     const uint32_t n_tiles = (b.n_reads + kKcReadsPerTile - 1) / kKcReadsPerTile;
     unsigned long long st_windows = 0, st_counted = 0, st_long = 0;
     uint32_t st_full = 0;
@@ -245,68 +193,37 @@ kc_count_kernel(KcView t, BatchView b, uint32_t parent, KcStats* __restrict__ st
                 set_bits(s_bad, hi - lo, nseg * 16u);
             }
             __syncthreads();
-            // (c)  Two loops per 16-position word.  The first stays CONVERGED and does the arithmetic that is the same
-            // for every lane: rolling m-mers, their hashes, the sliding minimum -> the home line of each position.
-            // The second does the table accesses and is allowed to diverge: the probe loops of kc_insert take a
-            // different number of dependent L2 / HBM round trips per lane, and independent thread scheduling lets the
-            // lanes of a warp wait for theirs side by side (in lockstep, capture r02_j, the kernel ran at 6 % issue
-            // utilisation; with the arithmetic inside the divergent loop, capture r02_i, each lane executed it alone).
-            for (uint32_t wbase = 0; wbase < nseg; wbase += kTileThreads) {
-                const uint32_t wi = min(wbase + tid, nseg - 1u);
-                uint32_t valid = 0;
-                if (wbase + tid < nseg) valid = ~(s_bad[wi >> 1] >> ((wi & 1u) * 16u)) & 0xFFFFu;
-                if (!__any_sync(0xFFFFFFFFu, valid != 0u)) continue;
+            // (c)
+            for (uint32_t wi = tid; wi < nseg; wi += kTileThreads) {
+                uint32_t valid = ~(s_bad[wi >> 1] >> ((wi & 1u) * 16u)) & 0xFFFFu;
+                if (!valid) continue;
                 st_windows += __popc(valid);
                 const uint32_t w0 = s_packed[wi], w1 = s_packed[wi + 1];
                 const uint32_t nxt = __funnelshift_l(s_packed[wi + nxt_word + 1], s_packed[wi + nxt_word], nxt_sh);
                 const uint64_t x = ((uint64_t)w0 << 32) | w1;
-                uint64_t y = __brevll(~x);
-                y = ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
-                uint32_t ml[16];                       // home line (number) of every position
-                uint32_t mine = 0;                     // positions that are valid and belong to this partition
-                {
-                    uint64_t fm = mm1 ? (x >> (64u - 2u * (uint32_t)mm1)) : 0ull;
-                    uint64_t rm = (y & mask_mm1) << 2;
-                    uint32_t hq[8];                    // hashes of the last eight canonical m-mers, newest first
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) hq[q] = 0xFFFFFFFFu;
-                    for (int i = mm1; i < km1; ++i) {  // bases m-1 .. k-2 complete the first mw - 1 m-mers
-                        const uint32_t c = (uint32_t)(x >> (62 - 2 * i)) & 3u;
-                        fm = ((fm << 2) | c) & mmask;
-                        rm = (rm >> 2) | ((uint64_t)(c ^ 3u) << rm_shift);
-#pragma unroll
-                        for (int q = 7; q > 0; --q) hq[q] = hq[q - 1];
-                        hq[0] = kc_hash_m(fm < rm ? fm : rm);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t c = (nxt >> (30 - 2 * j)) & 3u;
-                        fm = ((fm << 2) | c) & mmask;
-                        rm = (rm >> 2) | ((uint64_t)(c ^ 3u) << rm_shift);
-#pragma unroll
-                        for (int q = 7; q > 0; --q) hq[q] = hq[q - 1];
-                        hq[0] = kc_hash_m(fm < rm ? fm : rm);
-                        uint32_t hmin = hq[0];         // the k-mer's mw m-mers are the newest mw entries
-#pragma unroll
-                        for (int q = 1; q < 8; ++q) hmin = min(hmin, hq[q] | keep[q]);
-                        const uint64_t mix = kc_mix_mini(hmin);
-                        ml[j] = (uint32_t)mix;
-                        if (t.n_parts == 1u || kc_part_of(mix, t.n_parts) == t.part) mine |= 1u << j;
-                    }
-                }
-                mine &= valid;
-                st_counted += __popc(mine);
-                __syncwarp();
                 uint64_t fwd = km1 ? (x >> fwd_init_shift) : 0ull;
-                uint64_t rcv = (y & mask_km1) << 2;    // reverse complement of the first k-1 bases, one base up
-#pragma unroll
+                // reverse complement of the first k-1 bases (complement = ^3 in this code), shifted up by
+                // one base so that the first roll lands it in place
+                uint64_t rcv;
+                {
+                    uint64_t y = __brevll(~x);
+                    y = ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+                    rcv = (y & mask_km1) << 2;
+                }
+#pragma unroll 4
                 for (int j = 0; j < 16; ++j) {
                     const uint32_t c = (nxt >> (30 - 2 * j)) & 3u;
                     fwd = ((fwd << 2) | c) & kmask;
                     rcv = (rcv >> 2) | ((uint64_t)(c ^ 3u) << rc_shift);
-                    if ((mine >> j) & 1u) kc_insert(t, fwd < rcv ? fwd : rcv, (uint64_t)ml[j], parent, st_full);
+                    if ((valid >> j) & 1u) {
+                        const uint64_t canon = fwd < rcv ? fwd : rcv;
+                        const uint64_t mix = kc_mix(canon);
+                        if (t.n_parts == 1u || kc_part_of(mix, t.n_parts) == t.part) {
+                            ++st_counted;
+                            kc_insert(t, canon, mix, parent, st_full);
+                        }
+                    }
                 }
-                __syncwarp();
             }
             ra = rb;
         }
