@@ -134,10 +134,20 @@ int run_classify(const Options& opt, RunStats& st) {
     fprintf(stderr, " use %d GPU(s), %d parser thread(s)\n", n_gpu, opt.threads);
     logtime();
 
+    // CUDA start-up stays on this thread, before any other thread exists: context creation maps and unmaps memory,
+    // and with a dozen parser and decoder threads faulting pages at the same time it took 1.1-1.4 s instead of 0.3
+    // (profiles/bench_r02_p_cli16m.json, the build that overlapped it).
+    for (int g = 0; g < n_gpu && !parse_only; ++g)
+        if (hast_create(g, &ctx[(size_t)g]) != HAST_OK) {
+            fprintf(stderr, "ERROR : %s\n", hast_last_error(nullptr));
+            cleanup();
+            return 1;
+        }
+
     // ---- k-mer table (load_kmers x2 + InitAdaptor, classify.cpp:433-437) -----------
-    // Built on its own thread -- CUDA start-up, the two list files, the inserts, the clones -- WHILE the readers and
-    // parsers below already fill batches: parsing needs no table, only the first kernel launch does.  The GPU threads
-    // wait for `table_ready`; a failure here aborts the pipeline like any other stage's.
+    // Built on its own thread -- the two list files, the inserts, the clones -- WHILE the readers and parsers below
+    // already fill batches: parsing needs no table, only the first kernel launch does.  The GPU threads wait for
+    // `table_ready`; a failure here aborts the pipeline like any other stage's.
     std::mutex tb_mu;
     std::condition_variable tb_cv;
     bool table_ready = parse_only, table_failed = false;
@@ -147,8 +157,6 @@ int run_classify(const Options& opt, RunStats& st) {
     do {                                                                    \
         if ((call) != HAST_OK) return std::string(hast_last_error(c));      \
     } while (0)
-        for (int g = 0; g < n_gpu; ++g)
-            if (hast_create(g, &ctx[(size_t)g]) != HAST_OK) return std::string(hast_last_error(nullptr));
         KmerList l0, l1;
         fprintf(stderr, "__load hap0 kmers__\n");
         std::string e = load_kmer_list(opt.hap0, 0, 0, l0);
