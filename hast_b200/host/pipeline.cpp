@@ -145,13 +145,7 @@ int run_classify(const Options& opt, RunStats& st) {
         }
 
     // ---- k-mer table (load_kmers x2 + InitAdaptor, classify.cpp:433-437) -----------
-    // Built on its own thread -- the two list files, the inserts, the clones -- WHILE the readers and parsers below
-    // already fill batches: parsing needs no table, only the first kernel launch does.  The GPU threads wait for
-    // `table_ready`; a failure here aborts the pipeline like any other stage's.
-    std::mutex tb_mu;
-    std::condition_variable tb_cv;
-    bool table_ready = parse_only, table_failed = false;
-    std::string table_err;
+    // (a lambda because it was also tried on a thread of its own, see below where it is called)
     auto build_table = [&]() -> std::string {
 #define TCHECK(c, call)                                                     \
     do {                                                                    \
@@ -273,20 +267,14 @@ int run_classify(const Options& opt, RunStats& st) {
         }
         streams.push_back(path);
     }
-    std::thread table_thread;
-    if (!parse_only)
-        table_thread = std::thread([&] {
-            const std::string e = build_table();
-            {
-                std::lock_guard<std::mutex> lk(tb_mu);
-                if (e.empty()) table_ready = true;
-                else { table_failed = true; table_err = e; }
-            }
-            if (!e.empty()) { sh.fail(e); abort_all(); }
-            tb_cv.notify_all();
-        });
-    // join before any early return below destroys what the thread uses
-    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } table_joiner{table_thread};
+    // The table is built BEFORE the pipeline threads start.  Overlapping the two was measured (profiles/bench_r02_{f,p,q}_cli*.json):
+    // it saves 0.3 s on a 4 M-pair input when it works, but with a dozen parser and sixteen decoder threads competing for the
+    // cores and the memory system the table build itself took anything from 0.4 to 1.7 s instead of a steady 0.4-0.5 s, and
+    // for inputs of useful size the overlap is worth 2 % at best.
+    if (!parse_only) {
+        const std::string e = build_table();
+        if (!e.empty()) { fprintf(stderr, "ERROR : %s\n", e.c_str()); free_batches(); cleanup(); return 1; }
+    }
     std::atomic<size_t> next_file{0};
     const int n_readers = (int)std::min<size_t>({streams.size(), (size_t)opt.threads, (size_t)8});
     // threads per gzip stream (inflate_par.h: one replays, the others entropy-decode).  Measured on a 16-core box with
@@ -386,11 +374,6 @@ int run_classify(const Options& opt, RunStats& st) {
                 q_batch_free.push(b);
             }
             if (parse_only) return;
-            {                                                  // parsing runs ahead; the first launch needs the table
-                std::unique_lock<std::mutex> lk(tb_mu);
-                tb_cv.wait(lk, [&] { return table_ready || table_failed; });
-                if (table_failed) return;
-            }
             hast_ctx* c = ctx[(size_t)g];
             while (q_batch.pop(b)) {
                 const uint64_t need = (uint64_t)b->max_barcode + 1;
@@ -421,7 +404,6 @@ int run_classify(const Options& opt, RunStats& st) {
     for (auto& t : readers) t.join();
     for (auto& t : parsers) t.join();
     for (auto& t : gpu_threads) t.join();
-    if (table_thread.joinable()) table_thread.join();
     if (sh.failed) {
         fprintf(stderr, "ERROR : %s\n", sh.error.c_str());
         free_batches(); cleanup();
