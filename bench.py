@@ -192,6 +192,7 @@ class RefRunner:
             self.one, _ = trio.write_fastq(workdir, gz=False, lo=0, hi=1, stem="one")
             if gz_too:                       # one gzip member per file, level 6: what a sequencer ships
                 self.gz = trio.write_fastq(workdir / "gz", gz=6, lo=0, hi=self.sample, stem="sample")
+            os.sync()                        # timed legs read clean page-cache pages, not files still being written back
         else:
             sys.path.insert(0, str(ROOT / "tests"))
             import oracle as orc

@@ -56,6 +56,7 @@ def main():
         pat, mat = trio.write_kmer_lists(d)
         r1, r2 = trio.write_fastq(d, gz=False)
         gz = list(trio.write_fastq(d / "gz", gz=6))            # one gzip member per file, level 6, like a sequencer's output
+        os.sync()                                              # the legs read clean page-cache pages, not files still being written back
         out["fastq_bytes"] = os.path.getsize(r1) + os.path.getsize(r2)
         out["gz_bytes"] = sum(os.path.getsize(p) for p in gz)
         exe = str(ROOT / "bin" / "classify")
