@@ -173,3 +173,22 @@ def test_merge_result_intended_mode(tmp_path):
     out = tmp_path / "o.tsv"
     assert orc.merge_result([tmp_path / "a.tsv", tmp_path / "b.tsv"], out, 1.0, 2.0, intended=True) == 0
     assert out.read_bytes() == r.stdout
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the reference's own CPU path, oracle/_ref when the reference compiled here, else the
+    oracle port): one JSON line with the keys the driver reads, no GPU needed."""
+    import sys
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "small", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-600:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "impl", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "pairs/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
