@@ -226,6 +226,35 @@ int launch_tile(hast_ctx* ctx, int mode, const BatchView& bv_in, uint64_t* d_kme
     return HAST_OK;
 }
 
+// Both loaders stream their input through TWO halves of the scratch buffer: the insert kernel of one chunk runs while
+// the next chunk is being copied (a 62 M-key list is 1.4 GB of text; round 1 synchronised after every chunk).
+template <class Launch>
+int stream_chunks(hast_ctx* ctx, const char* src, uint64_t n_items, uint64_t item_bytes, uint64_t chunk_items, Launch launch) {
+    const size_t half = (size_t)(chunk_items * item_bytes + 255) & ~(size_t)255;
+    int rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, 2 * half);
+    if (rc) return rc;
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    for (auto& e : done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int h = 0;
+    cudaError_t err = cudaSuccess;
+    for (uint64_t at = 0; at < n_items && err == cudaSuccess; at += chunk_items, h ^= 1) {
+        const uint64_t n = std::min(chunk_items, n_items - at);
+        char* d = (char*)ctx->d_scratch + (size_t)h * half;
+        err = cudaEventSynchronize(done[h]);                       // the kernel that last read this half (no-op the first time)
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d, src + at * item_bytes, n * item_bytes, cudaMemcpyHostToDevice, ctx->hs);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->hs);   // pageable source: the caller may free it after we return
+        if (err != cudaSuccess) break;
+        ctx->st.h2d_bytes += n * item_bytes;
+        launch(d, n);
+        err = cudaGetLastError();
+        ctx->st.kernel_launches++;
+        if (err == cudaSuccess) err = cudaEventRecord(done[h], ctx->cs);
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->cs);
+    for (auto& e : done) cudaEventDestroy(e);
+    if (err != cudaSuccess) return fail(ctx, HAST_E_CUDA, std::string("table load: ") + cudaGetErrorString(err));
+    return HAST_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -471,20 +500,13 @@ int hast_table_add_text(hast_ctx* ctx, const char* text, uint64_t n_lines, int p
     if (!n_lines) return HAST_OK;
     if (!text) return fail(ctx, HAST_E_ARG, "text is NULL");
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->cs));                            // hast_table_begin's memsets
     const uint64_t stride = (uint64_t)ctx->tv.k + 1;
-    const uint64_t chunk_lines = std::max<uint64_t>(1, ((uint64_t)256 << 20) / stride);
-    for (uint64_t done = 0; done < n_lines; done += chunk_lines) {
-        const uint64_t n = std::min(chunk_lines, n_lines - done);
-        int rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, n * stride);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(ctx->d_scratch, text + done * stride, n * stride, cudaMemcpyHostToDevice, ctx->cs));
-        ctx->st.h2d_bytes += n * stride;
-        table_insert_text_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->cs>>>(
-            ctx->tv, (const char*)ctx->d_scratch, n, (uint32_t)parent, ctx->d_stats);
-        CU(cudaGetLastError());
-        ctx->st.kernel_launches++;
-        CU(cudaStreamSynchronize(ctx->cs));        // the scratch buffer is reused by the next chunk
-    }
+    const uint64_t chunk_lines = std::max<uint64_t>(1, ((uint64_t)128 << 20) / stride);
+    int rc = stream_chunks(ctx, text, n_lines, stride, chunk_lines, [&](char* d, uint64_t n) {
+        table_insert_text_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->cs>>>(ctx->tv, d, n, (uint32_t)parent, ctx->d_stats);
+    });
+    if (rc) return rc;
     return table_check(ctx);
 }
 
@@ -495,19 +517,11 @@ int hast_table_add_packed(hast_ctx* ctx, const uint64_t* kmers, uint64_t n, int 
     if (!n) return HAST_OK;
     if (!kmers) return fail(ctx, HAST_E_ARG, "kmers is NULL");
     CU(cudaSetDevice(ctx->device));
-    const uint64_t chunk = (uint64_t)32 << 20;
-    for (uint64_t done = 0; done < n; done += chunk) {
-        const uint64_t m = std::min(chunk, n - done);
-        int rc = ensure(ctx, &ctx->d_scratch, &ctx->cap_scratch, m * 8);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(ctx->d_scratch, kmers + done, m * 8, cudaMemcpyHostToDevice, ctx->cs));
-        ctx->st.h2d_bytes += m * 8;
-        table_insert_packed_kernel<<<grid_for(ctx, m, 256), 256, 0, ctx->cs>>>(
-            ctx->tv, (const uint64_t*)ctx->d_scratch, m, (uint32_t)parent, ctx->d_stats);
-        CU(cudaGetLastError());
-        ctx->st.kernel_launches++;
-        CU(cudaStreamSynchronize(ctx->cs));
-    }
+    CU(cudaStreamSynchronize(ctx->cs));
+    int rc = stream_chunks(ctx, (const char*)kmers, n, 8, (uint64_t)16 << 20, [&](char* d, uint64_t m) {
+        table_insert_packed_kernel<<<grid_for(ctx, m, 256), 256, 0, ctx->cs>>>(ctx->tv, (const uint64_t*)d, m, (uint32_t)parent, ctx->d_stats);
+    });
+    if (rc) return rc;
     return table_check(ctx);
 }
 
