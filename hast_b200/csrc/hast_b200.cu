@@ -81,16 +81,13 @@ bool nccl_load() {
 
 }  // namespace
 
-constexpr int kFinishParts = 4;
-
 struct hast_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t cs = nullptr;            // compute stream
     cudaStream_t hs = nullptr;            // host-to-device copy stream
     cudaEvent_t t0 = nullptr, t1 = nullptr;
-    cudaEvent_t f0 = nullptr, f1 = nullptr, f2 = nullptr;   // hast_finish: reduce / read-back timing
-    cudaEvent_t fpart[4] = {nullptr, nullptr, nullptr, nullptr};   // ... one per piece of the reduce
+    cudaEvent_t f0 = nullptr, f1 = nullptr;   // hast_finish: reduce / read-back timing
 
     TableView tv{};
     uint64_t n_buckets = 0;
@@ -296,8 +293,6 @@ int hast_create(int device, hast_ctx** out) {
     CU_NEW(cudaEventCreate(&ctx->t1));
     CU_NEW(cudaEventCreate(&ctx->f0));
     CU_NEW(cudaEventCreate(&ctx->f1));
-    CU_NEW(cudaEventCreate(&ctx->f2));
-    for (auto& ev : ctx->fpart) CU_NEW(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& s : ctx->slot) {
         CU_NEW(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
         CU_NEW(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -365,8 +360,6 @@ void hast_destroy(hast_ctx* ctx) {
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->f0) cudaEventDestroy(ctx->f0);
     if (ctx->f1) cudaEventDestroy(ctx->f1);
-    if (ctx->f2) cudaEventDestroy(ctx->f2);
-    for (auto& e : ctx->fpart) if (e) cudaEventDestroy(e);
     if (ctx->cs) cudaStreamDestroy(ctx->cs);
     if (ctx->hs) cudaStreamDestroy(ctx->hs);
     delete ctx;
@@ -827,44 +820,26 @@ int hast_finish(hast_ctx* ctx, int32_t* counts_out, uint64_t n_barcodes) {
     if (ds.bad_barcode)
         return fail(ctx, HAST_E_ARG, std::to_string(ds.bad_barcode) + " read(s) with barcode id >= reserved barcodes");
     if (n_barcodes > ctx->n_barcodes) return fail(ctx, HAST_E_ARG, "n_barcodes exceeds reserved barcodes");
+    const int32_t* src = ctx->d_counts;
     float ms = 0.f;
-    const bool want = counts_out && n_barcodes && ctx->rank == 0;
     if (ctx->comm) {
         if (n_barcodes > ctx->cap_reduced) {
             if (ctx->d_reduced) CU(cudaFree(ctx->d_reduced));
             CU(cudaMalloc(&ctx->d_reduced, std::max<uint64_t>(n_barcodes, 1) * 2 * sizeof(int32_t)));
             ctx->cap_reduced = n_barcodes;
         }
-        // BarcodeCache::Add (classify.cpp:57-63) across GPUs: an int32 sum to rank 0.  The array goes in kFinishParts
-        // pieces so that rank 0 reads piece i back to the host (copy stream) while piece i+1 is still being reduced:
-        // at 20 M barcodes both steps take ~3 ms on eight GPUs, and only one of them is exposed.
-        const uint64_t n_elem = n_barcodes * 2;
-        const uint64_t per = (n_elem + kFinishParts - 1) / kFinishParts;
+        // BarcodeCache::Add (classify.cpp:57-63) across GPUs: one int32 sum to rank 0
         CU(cudaEventRecord(ctx->f0, ctx->cs));
-        for (int p = 0; p < kFinishParts; ++p) {
-            const uint64_t lo = std::min<uint64_t>(n_elem, (uint64_t)p * per), hi = std::min<uint64_t>(n_elem, lo + per);
-            if (hi == lo) continue;
-            NC(g_nccl.Reduce(ctx->d_counts + lo, ctx->d_reduced + lo, hi - lo, ncclInt32, ncclSum, 0, ctx->comm, ctx->cs));
-            if (want) {
-                CU(cudaEventRecord(ctx->fpart[p], ctx->cs));
-                CU(cudaStreamWaitEvent(ctx->hs, ctx->fpart[p], 0));
-                CU(cudaMemcpyAsync(counts_out + lo, ctx->d_reduced + lo, (hi - lo) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->hs));
-            }
-        }
+        NC(g_nccl.Reduce(ctx->d_counts, ctx->d_reduced, n_barcodes * 2, ncclInt32, ncclSum, 0, ctx->comm, ctx->cs));
         CU(cudaEventRecord(ctx->f1, ctx->cs));
-        if (want) CU(cudaEventRecord(ctx->f2, ctx->hs));
         CU(cudaStreamSynchronize(ctx->cs));
         CU(cudaEventElapsedTime(&ms, ctx->f0, ctx->f1));
         ctx->st.finish_reduce_us += (uint64_t)(ms * 1000.f);
-        if (want) {
-            CU(cudaStreamSynchronize(ctx->hs));
-            CU(cudaEventElapsedTime(&ms, ctx->f1, ctx->f2));       // the part of the read-back the reduce did not hide
-            ctx->st.finish_d2h_us += (uint64_t)(std::max(ms, 0.f) * 1000.f);
-            ctx->st.d2h_bytes += n_barcodes * 2 * sizeof(int32_t);
-        }
-    } else if (want) {
+        src = ctx->d_reduced;
+    }
+    if (counts_out && n_barcodes && ctx->rank == 0) {
         CU(cudaEventRecord(ctx->f0, ctx->cs));
-        CU(cudaMemcpyAsync(counts_out, ctx->d_counts, n_barcodes * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cs));
+        CU(cudaMemcpyAsync(counts_out, src, n_barcodes * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->cs));
         CU(cudaEventRecord(ctx->f1, ctx->cs));
         CU(cudaStreamSynchronize(ctx->cs));
         CU(cudaEventElapsedTime(&ms, ctx->f0, ctx->f1));
