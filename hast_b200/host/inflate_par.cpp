@@ -757,7 +757,10 @@ void ParallelGzip::launch(Batch& b, Pool& pool, uint64_t next_start, bool at_fil
             pool.submit([this, &b, &pool, in, n, oi] {
                 std::vector<uint64_t> targets;
                 for (size_t o = oi + 1; o < b.order.size(); ++o) targets.push_back(b.chunks[b.order[o]].start_bit);
+                const auto t0 = std::chrono::steady_clock::now();
                 decode_chunk(in, n, b.chunks[b.order[oi]], targets, b.soft_stop, chunk_bytes_);
+                decode_ns_.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
+                                     std::memory_order_relaxed);
                 if (b.decodes_left.fetch_sub(1) == 1) {
                     { std::lock_guard<std::mutex> lk(pool.mu); b.ready = true; }
                     pool.cv_done.notify_all();
@@ -792,7 +795,7 @@ void ParallelGzip::run() {
     double t_ph[4] = {0, 0, 0, 0};
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     uint64_t n_tok_total = 0, n_lit_total = 0;
-    struct ProfOut { bool on; double* t; uint64_t* a; uint64_t* b2; ~ProfOut() { if (on) fprintf(stderr, "coordinator: wait-for-decode %.3f replay %.3f crc-wait %.3f emit %.3f s; %llu tokens, %llu literal bytes\n", t[0], t[1], t[2], t[3], (unsigned long long)*a, (unsigned long long)*b2); } } prof_out{prof, t_ph, &n_tok_total, &n_lit_total};
+    struct ProfOut { bool on; double* t; uint64_t* a; uint64_t* b2; std::atomic<uint64_t>* dn; ~ProfOut() { if (on) fprintf(stderr, "coordinator: wait-for-decode %.3f replay %.3f crc-wait %.3f emit %.3f s; workers' entropy decode %.3f s; %llu tokens, %llu literal bytes\n", t[0], t[1], t[2], t[3], dn->load() * 1e-9, (unsigned long long)*a, (unsigned long long)*b2); } } prof_out{prof, t_ph, &n_tok_total, &n_lit_total, &decode_ns_};
     std::atomic<int> crc_left{0};
     Pool pool(n_workers);                                      // declared last: joins its threads before the batches go
     int cur = 0;

@@ -23,6 +23,7 @@
 // a block boundary; a candidate it runs past is dropped and its chunk is decoded by the predecessor.
 // Output bytes are identical to GzipInflater's (tests/test_inflate.py runs both on every case).
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <cstddef>
 #include <cstdint>
@@ -101,6 +102,7 @@ private:
     bool done_ = false, stop_ = false;
     Piece current_;
     uint64_t member_out_checked_ = 0;
+    std::atomic<uint64_t> decode_ns_{0};       // time the workers spent in entropy decoding (HAST_PAR_PROF)
     struct BufferPool { std::mutex mu; std::vector<Buffer> spare; };
     std::shared_ptr<BufferPool> pool_ = std::make_shared<BufferPool>();   // output buffers handed back, reused by the replay
     std::string err_, err_pending_;
