@@ -87,7 +87,11 @@ int          hast_device(const hast_ctx *ctx);
  * fused kernel to the window rule of HAST stage 03 (03.mkoutput_by_fabulous2.0/
  * src_main/classify.cpp:203-218, string k-mers): a k-mer position votes iff all
  * its k bytes are upper-case A/C/G/T, other bytes do not silence the rest of the
- * sequence, and sequences shorter than k are not an error.                     */
+ * sequence, and sequences shorter than k are not an error.
+ * Launch-side knobs, effective at once: "reads_per_tile" (0, the default = as many
+ * reads as fill one pass of the fused kernel; 1..416 fixes it), "l2_persist_bytes"
+ * (L2 set aside for the pre-filter's evict_last loads, device-wide; default 64 MiB,
+ * clamped to the device maximum), "l2_fetch_granularity" (32 / 64 / 128).       */
 int          hast_set_option(hast_ctx *ctx, const char *name, int64_t value);
 /* pinned host memory for batch buffers */
 int          hast_host_alloc(void **ptr, size_t bytes);

@@ -125,6 +125,23 @@ def test_plain_files_sliced_across_threads_frame_like_getline(tmp_path, slice_by
     assert want_a == parse_only([tmp_path / "a.fq"], threads=3)             # default slice size
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_sliced_reader_equals_serial_reader_on_byte_soup(tmp_path, seed):
+    """Framing is by newline count alone, so ANY byte string must frame the same way in the sliced reader and in the
+    serial one: random printable soup with newlines at random places, blank lines, very long lines, no final newline."""
+    rng = np.random.default_rng(1000 + seed)
+    alphabet = np.frombuffer(b"ACGTN@+#/_0123456789acgt \t\r", np.uint8)
+    n = int(rng.integers(20_000, 200_000))
+    soup = alphabet[rng.integers(0, alphabet.size, n)].copy()
+    soup[rng.random(n) < (0.002 if seed % 2 else 0.05)] = ord("\n")
+    if seed % 3 == 0:
+        soup[-1] = ord("\n")
+    (tmp_path / "s.fq").write_bytes(soup.tobytes())
+    want = parse_only([tmp_path / "s.fq"], serial=True)
+    for slice_bytes in (1, 13, 4099, int(rng.integers(2, 70_000))):
+        assert parse_only([tmp_path / "s.fq"], threads=4, slice_bytes=slice_bytes) == want, slice_bytes
+
+
 def test_tiny_records_fill_a_batch_before_the_block_ends(tmp_path):
     """Records far shorter than the batch buffers were sized for: the block is parsed into several batches."""
     n = 700_000
