@@ -566,6 +566,38 @@ def leg_cfg2(args, R):
                "h2d_gbs_per_gpu": h2d / dt / 1e9,        # against ~55 GB/s of a PCIe Gen5 x16 link: this leg is PCIe-bound
                "path": "hast_submit_batch (pinned host buffers, double-buffered cudaMemcpyAsync) + hast_finish",
                "counts_identical_to_device_path": True}
+
+        # ---- the same ASCII host buffers, packed to 2 bits by the library on the host's cores (option host_pack_threads):
+        #      pack + H2D of a quarter of the bytes + kernel + read-back, all inside the timed region ----
+        if args.kernel >= 1 and args.host_pack_threads != 0:
+            cores = os.cpu_count() or 1
+            hp = args.host_pack_threads if args.host_pack_threads > 0 else max(1, cores // world - 2)
+            eng.set_option("host_pack_threads", hp)
+
+            def step_hp():
+                for b in hb:
+                    eng.submit_batch_ptr(*b)
+                return eng.finish(nb, want_counts=(rank == 0))
+
+            for _ in range(2):
+                eng.reset_counts()
+                c_q = step_hp()
+            eng.reset_counts()
+            R.barrier()
+            t = time.perf_counter()
+            for _ in range(args.steps):
+                c_q = step_hp()
+            eng.sync()
+            dtq = R.max_over_ranks((time.perf_counter() - t) / args.steps)
+            R.barrier()
+            eng.set_option("host_pack_threads", 0)
+            if rank == 0:
+                assert (c_q == counts).all(), "host-packed path and device-resident path disagree"
+            h2d_q = (n_reads * L + 15) // 16 * 4 + sum(b[4] + 1 for b in hb) * 4 + n_reads * 4 + (n_reads + 31) // 32 * 4
+            e2e["host_packed"] = {"value": world * P / dtq, "unit": UNIT, "h2d_bytes_per_step": int(h2d_q),
+                                  "d2h_bytes_per_step": int(nb * 8), "ms_per_step": dtq * 1e3, "host_pack_threads": hp,
+                                  "path": "hast_submit_batch with option host_pack_threads: the same ASCII host buffers, packed to "
+                                          "2 bits on the host's cores inside the call (and the timed region), a quarter of the bytes copied"}
         del h_bases
 
         # ---- the same step with batches as the C++ parser hands them over by default: 2-bit packed ----
@@ -895,6 +927,7 @@ def main():
     ap.add_argument("--filter-max-mib", type=int, default=64, help="pre-filter size cap (MiB)")
     ap.add_argument("--reads-per-tile", type=int, default=0, help="fused kernel: reads per tile (0 = what fills one pass)")
     ap.add_argument("--l2-persist-mib", type=int, default=-1, help="tuning: L2 set-aside for persisting accesses (MiB); -1 = leave")
+    ap.add_argument("--host-pack-threads", type=int, default=-1, help="e2e.host_packed leg: host threads that pack (-1 = cores/ranks - 2, 0 = skip the leg)")
     ap.add_argument("--only-cfg3", action="store_true", help="tuning: run the cfg3 leg alone and print its object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "hast_b200" else args.warmup

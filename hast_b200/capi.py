@@ -77,6 +77,7 @@ SIGNATURES = {
     "hast_submit_batch_device": (_i32, [_vp, _vp, _u64, _vp, _vp, _u32]),
     "hast_submit_batch_packed": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _u32, C.POINTER(_u64)]),
     "hast_submit_batch_packed_device": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _u32]),
+    "hast_pack_bases": (_i32, [_vp, _u64, _vp, _u32, _vp, _vp, _i32]),
     "hast_sync": (_i32, [_vp]),
     "hast_finish": (_i32, [_vp, _vp, _u64]),
     "hast_stats_get": (_i32, [_vp, C.POINTER(Stats)]),
@@ -152,6 +153,20 @@ def pack_bases(bases: np.ndarray, read_off: np.ndarray):
     bits[:n_reads] = flag
     has_n = np.packbits(bits.reshape(-1, 32)[:, ::-1], axis=1).view(">u4").astype(np.uint32).reshape(-1)
     return np.ascontiguousarray(words), np.ascontiguousarray(has_n if has_n.size else np.zeros(1, np.uint32))
+
+
+def pack_bases_native(bases: np.ndarray, read_off: np.ndarray, threads: int = 1):
+    """hast_pack_bases: the library's own host packer (no device needed) -> (words, has_n)"""
+    lib = load_library()
+    bases = np.ascontiguousarray(bases, np.uint8).reshape(-1)
+    read_off = np.ascontiguousarray(read_off, np.uint32)
+    n_reads = read_off.size - 1
+    words = np.empty((bases.size + 15) // 16, np.uint32)
+    has_n = np.zeros(max(1, (n_reads + 31) // 32), np.uint32)
+    rc = lib.hast_pack_bases(_ptr(bases), bases.size, _ptr(read_off), n_reads, _ptr(words), _ptr(has_n), threads)
+    if rc:
+        raise HastError(rc, (lib.hast_last_error(None) or b"").decode())
+    return words, has_n
 
 
 class Engine:

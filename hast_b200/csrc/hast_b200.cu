@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 #include "fused.cuh"
 #include "kcount.cuh"
+#include "host_pack.h"
 #include <cub/device/device_radix_sort.cuh>
 
 using namespace hast;
@@ -34,6 +35,9 @@ struct Slot {
     uint32_t* d_bc = nullptr;    size_t cap_bc = 0;
     uint32_t* d_hasn = nullptr;  size_t cap_hasn = 0;
     cudaEvent_t copied = nullptr, done = nullptr;
+    // pinned staging of a batch packed on the host (option host_pack_threads)
+    uint32_t* h_packed = nullptr; size_t cap_h_packed = 0;
+    uint32_t* h_hasn = nullptr;   size_t cap_h_hasn = 0;
 };
 
 // ---- NCCL through dlopen: a single-GPU run never needs the library ---------
@@ -118,6 +122,7 @@ struct hast_ctx {
                                           // mini_len(k) != 0 in table.cuh; every other k -- 17 included -- runs as 1), 4 = as 3 with TMA-staged reads,
                                           // 1 = classify_kernel (per-k-mer filter word), 2 = same with TMA-staged reads, 0 = tile_kernel<MODE_CLASSIFY>
     int64_t opt_seq_mode = 0;             // 1 = stage-03 window rule (classify_kernel<.., SEQ>)
+    hastpack::Pool* pack_pool = nullptr;  // option host_pack_threads > 0: hast_submit_batch packs ASCII batches to 2 bits on the host
     int64_t l2_persist = -1;              // bytes of L2 set aside for persisting accesses (option l2_persist_bytes); -1 = default
     int64_t opt_reads_per_tile = 0;       // 0 = per batch, what fills one pass (fused_reads_per_tile); else fixed (tuning / tests)
     int64_t opt_filter_bits_per_key = 16;
@@ -343,8 +348,11 @@ void hast_destroy(hast_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->pack_pool) hastpack::pool_destroy(ctx->pack_pool);
     for (auto& s : ctx->slot) {
         cudaFree(s.d_bases); cudaFree(s.d_off); cudaFree(s.d_bc); cudaFree(s.d_hasn);
+        if (s.h_packed) cudaFreeHost(s.h_packed);
+        if (s.h_hasn) cudaFreeHost(s.h_hasn);
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -397,6 +405,12 @@ int hast_set_option(hast_ctx* ctx, const char* name, int64_t value) {
         if (value != 32 && value != 64 && value != 128) return fail(ctx, HAST_E_ARG, "l2_fetch_granularity: 32, 64 or 128");
         CU(cudaSetDevice(ctx->device));
         CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+    } else if (n == "host_pack_threads") {
+        // hast_submit_batch (ASCII host buffers): pack the batch to 2 bits on `value` host threads and send a quarter of
+        // the bytes over PCIe (what bin/classify's parser does while parsing).  0 = send the ASCII bytes (default).
+        if (value < 0 || value > 256) return fail(ctx, HAST_E_ARG, "host_pack_threads: 0..256");
+        if (ctx->pack_pool) { hastpack::pool_destroy(ctx->pack_pool); ctx->pack_pool = nullptr; }
+        if (value > 0) ctx->pack_pool = hastpack::pool_create((int)value);
     } else if (n == "l2_persist_bytes") {
         // device-wide: L2 set aside for persisting accesses (cudaLimitPersistingL2CacheSize).  The pre-filter words are
         // loaded with an L2 evict_last policy; without a set-aside the hardware has nowhere to keep them apart from the
@@ -664,6 +678,40 @@ int hast_submit_batch(hast_ctx* ctx, const uint8_t* bases, uint64_t n_bases, con
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slot[ctx->seq % kSlots];
     CU(cudaEventSynchronize(s.done));                   // the kernel that last used this slot
+    if (ctx->pack_pool && ctx->opt_kernel >= 1 && !ctx->opt_seq_mode) {
+        // pack on the host, copy a quarter of the bytes: the caller's buffer is consumed before this call returns
+        const size_t n_words = (size_t)((n_bases + 15) / 16), n_flag = ((size_t)n_reads + 31) / 32;
+        if (s.cap_h_packed < n_words * 4 + 16) {
+            if (s.h_packed) CU(cudaFreeHost(s.h_packed));
+            s.cap_h_packed = (n_words * 4 + 16) * 5 / 4;
+            CU(cudaHostAlloc((void**)&s.h_packed, s.cap_h_packed, cudaHostAllocPortable));
+        }
+        if (s.cap_h_hasn < n_flag * 4 + 16) {
+            if (s.h_hasn) CU(cudaFreeHost(s.h_hasn));
+            s.cap_h_hasn = (n_flag * 4 + 16) * 5 / 4;
+            CU(cudaHostAlloc((void**)&s.h_hasn, s.cap_h_hasn, cudaHostAllocPortable));
+        }
+        hastpack::pack_batch(ctx->pack_pool, bases, n_bases, read_off, n_reads, s.h_packed, s.h_hasn);
+        if ((rc = ensure(ctx, (void**)&s.d_bases, &s.cap_bases, n_words * 4 + 16))) return rc;
+        if ((rc = ensure(ctx, (void**)&s.d_off, &s.cap_off, ((size_t)n_reads + 1) * 4))) return rc;
+        if ((rc = ensure(ctx, (void**)&s.d_bc, &s.cap_bc, (size_t)n_reads * 4))) return rc;
+        if ((rc = ensure(ctx, (void**)&s.d_hasn, &s.cap_hasn, n_flag * 4))) return rc;
+        CU(cudaMemcpyAsync(s.d_bases, s.h_packed, n_words * 4, cudaMemcpyHostToDevice, ctx->hs));
+        CU(cudaMemcpyAsync(s.d_off, read_off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, ctx->hs));
+        CU(cudaMemcpyAsync(s.d_bc, barcode_id, (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->hs));
+        CU(cudaMemcpyAsync(s.d_hasn, s.h_hasn, n_flag * 4, cudaMemcpyHostToDevice, ctx->hs));
+        CU(cudaEventRecord(s.copied, ctx->hs));
+        CU(cudaStreamWaitEvent(ctx->cs, s.copied, 0));
+        BatchView pv{nullptr, s.d_off, s.d_bc, n_bases, n_reads, (const uint32_t*)s.d_bases, s.d_hasn};
+        if ((rc = launch_tile(ctx, MODE_CLASSIFY, pv, nullptr, nullptr))) return rc;
+        CU(cudaEventRecord(s.done, ctx->cs));
+        ctx->st.h2d_bytes += n_words * 4 + ((size_t)n_reads + 1) * 4 + (size_t)n_reads * 4 + n_flag * 4;
+        ctx->st.batches++;
+        ctx->st.reads += n_reads;
+        ctx->st.bases += n_bases;
+        ctx->seq++;
+        return HAST_OK;
+    }
     if ((rc = ensure(ctx, (void**)&s.d_bases, &s.cap_bases, n_bases + 16))) return rc;
     if ((rc = ensure(ctx, (void**)&s.d_off, &s.cap_off, ((size_t)n_reads + 1) * 4))) return rc;
     if ((rc = ensure(ctx, (void**)&s.d_bc, &s.cap_bc, (size_t)n_reads * 4))) return rc;
@@ -754,6 +802,18 @@ int hast_submit_batch_packed_device(hast_ctx* ctx, const uint32_t* d_packed, uin
     ctx->st.batches++;
     ctx->st.reads += n_reads;
     ctx->st.bases += n_bases;
+    return HAST_OK;
+}
+
+// stateless form of the host packer (tests; callers who want to pack ahead of hast_submit_batch_packed)
+int hast_pack_bases(const uint8_t* bases, uint64_t n_bases, const uint32_t* read_off, uint32_t n_reads,
+                    uint32_t* words_out, uint32_t* has_n_out, int threads) {
+    hast_ctx* ctx = nullptr;
+    if ((!bases && n_bases) || !read_off || !words_out || !has_n_out) return fail(ctx, HAST_E_ARG, "NULL argument");
+    if (n_bases >= 0xFFFFFFF0ull) return fail(ctx, HAST_E_ARG, "batch larger than 4 GiB of bases");
+    hastpack::Pool* p = threads > 1 ? hastpack::pool_create(threads) : nullptr;
+    hastpack::pack_batch(p, bases, n_bases, read_off, n_reads, words_out, has_n_out);
+    if (p) hastpack::pool_destroy(p);
     return HAST_OK;
 }
 

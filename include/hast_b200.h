@@ -91,7 +91,9 @@ int          hast_device(const hast_ctx *ctx);
  * Launch-side knobs, effective at once: "reads_per_tile" (0, the default = as many
  * reads as fill one pass of the fused kernel; 1..416 fixes it), "l2_persist_bytes"
  * (L2 set aside for the pre-filter's evict_last loads, device-wide; default 64 MiB,
- * clamped to the device maximum), "l2_fetch_granularity" (32 / 64 / 128).       */
+ * clamped to the device maximum), "l2_fetch_granularity" (32 / 64 / 128),
+ * "host_pack_threads" (0 = hast_submit_batch copies the ASCII bytes; N > 0 = it
+ * packs them to 2 bits on N host threads first and copies a quarter).           */
 int          hast_set_option(hast_ctx *ctx, const char *name, int64_t value);
 /* pinned host memory for batch buffers */
 int          hast_host_alloc(void **ptr, size_t bytes);
@@ -162,6 +164,14 @@ int hast_submit_batch_packed(hast_ctx *ctx, const uint32_t *packed, uint64_t n_b
 int hast_submit_batch_packed_device(hast_ctx *ctx, const uint32_t *d_packed, uint64_t n_bases,
                                     const uint32_t *d_read_off, const uint32_t *d_barcode_id,
                                     const uint32_t *d_has_n, uint32_t n_reads);
+/* The packing step on its own, on the host (no device, no context): ASCII bases ->
+ * the words and has_n bits hast_submit_batch_packed takes, on `threads` host
+ * threads.  Same code as kmer.h:11 (base2int) / :156-160 (MSB-first order) and
+ * containN, classify.cpp:182-185.  words_out: (n_bases + 15) / 16 words,
+ * has_n_out: (n_reads + 31) / 32 words.  With the option "host_pack_threads" > 0
+ * hast_submit_batch does this itself and copies a quarter of the bytes.          */
+int hast_pack_bases(const uint8_t *bases, uint64_t n_bases, const uint32_t *read_off,
+                    uint32_t n_reads, uint32_t *words_out, uint32_t *has_n_out, int threads);
 int hast_sync(hast_ctx *ctx);
 
 /* ---- finish: collect the per-barcode counts ---------------------------- */

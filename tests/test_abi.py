@@ -81,3 +81,23 @@ def test_sass_uses_256bit_sector_loads():
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in out.stdout or "SM100a" in out.stdout or "sm_100" in out.stdout
     assert re.search(r"LDG\.E\.[A-Z0-9.]*256", out.stdout)
+
+
+def test_bulk_packer_equals_reference_packing():
+    """hast_pack_bases (csrc/host_pack.cpp; what hast_submit_batch runs under the option host_pack_threads) needs no
+    device: it must give the words and containN bits of capi.pack_bases -- kmer.h:11 code, MSB-first, 'N' only upper
+    case (classify.cpp:182-185) -- for ragged, empty and tiny reads, on any number of threads."""
+    import numpy as np
+    from hast_b200 import capi
+    rng = np.random.default_rng(3)
+    letters = np.frombuffer(b"ACGTNacgtnRY\r", np.uint8)
+    for n_reads, L in ((1000, 100), (7, 3), (50_000, 151), (1, 1), (3, 16), (40, 0)):
+        lens = rng.integers(0, 2 * L + 1, n_reads) if n_reads > 1 else np.array([L])
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+        bases = letters[rng.integers(0, letters.size, int(off[-1]))].copy()
+        w0, h0 = capi.pack_bases(bases, off)
+        for threads in (1, 3, 8):
+            w1, h1 = capi.pack_bases_native(bases, off, threads)
+            assert np.array_equal(w0, w1), (n_reads, L, threads)
+            m = min(h0.size, h1.size)
+            assert np.array_equal(h0[:m], h1[:m]) and not h0[m:].any() and not h1[m:].any(), (n_reads, L, threads)

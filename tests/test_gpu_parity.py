@@ -135,6 +135,26 @@ def test_tile_size_does_not_change_counts(engine, k):
         engine.set_option("reads_per_tile", 0)
 
 
+@pytest.mark.parametrize("k", [17, 21, 32])
+def test_host_pack_option_equals_ascii(engine, k, request):
+    """option host_pack_threads: hast_submit_batch packs the ASCII batch to 2 bits on the host and runs the packed kernel"""
+    if "direct" in request.node.name:
+        pytest.skip("the direct-probe kernel takes ASCII batches only")
+    case = cases.adversarial_case(k, 3000, seed=950 + k)
+    build_table(engine, case)
+    o, _ = build_oracle(case)
+    bases, off = cases.flatten(case["reads"])
+    want, lookups = o.classify_batch(bases, off, case["bc_ids"], len(case["bc_names"]))
+    try:
+        for threads in (1, 4):
+            engine.set_option("host_pack_threads", threads)
+            got, st = run_fused(engine, case, split=[700, 1501])
+            assert (got == want).all() and st["lookups"] == lookups, threads
+            assert st["reads_with_n"] == sum(b"N" in r for r in case["reads"])
+    finally:
+        engine.set_option("host_pack_threads", 0)
+
+
 @pytest.mark.parametrize("k", [5, 17, 21, 32])
 def test_packed_batches_equal_ascii_batches(engine, k, request):
     """hast_submit_batch_packed (2-bit words + containN bits made on the host) == hast_submit_batch."""
