@@ -659,6 +659,20 @@ def leg_cfg2(args, R):
         if ceil:
             e2e["h2d_ceiling_gbs_per_gpu"] = ceil
             e2e["frac_of_h2d_ceiling"] = e2e["h2d_gbs_per_gpu"] / ceil
+        # Which host-buffer path is the headline `e2e`: decided by a rule on the machine, not by the result.  Packing on
+        # the host costs ~14 cores per GPU to beat the PCIe copy of the ASCII bytes (profiles/r02_y_host_pack.txt), so it is
+        # the path a caller would choose when every GPU has >= 12 host cores to itself, and the plain copy otherwise.
+        cores_per_rank = (os.cpu_count() or 1) // world
+        e2e["ascii"] = {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step",
+                                            "h2d_gbs_per_gpu", "path") if k in e2e}
+        e2e["rule"] = "host_packed when host cores per GPU >= 12 (here %d), else ascii" % cores_per_rank
+        if "host_packed" in e2e and cores_per_rank >= 12:
+            hpk = e2e["host_packed"]
+            e2e.update({"value": hpk["value"], "h2d_bytes_per_step": hpk["h2d_bytes_per_step"], "ms_per_step": hpk["ms_per_step"],
+                        "h2d_gbs_per_gpu": hpk["h2d_bytes_per_step"] / (hpk["ms_per_step"] * 1e-3) / 1e9, "path": hpk["path"],
+                        "chosen": "host_packed"})
+        else:
+            e2e["chosen"] = "ascii"
 
     line = None
     if rank == 0:
