@@ -659,20 +659,19 @@ def leg_cfg2(args, R):
         if ceil:
             e2e["h2d_ceiling_gbs_per_gpu"] = ceil
             e2e["frac_of_h2d_ceiling"] = e2e["h2d_gbs_per_gpu"] / ceil
-        # Which host-buffer path is the headline `e2e`: decided by a rule on the machine, not by the result.  Packing on
-        # the host costs ~14 cores per GPU to beat the PCIe copy of the ASCII bytes (profiles/r02_y_host_pack.txt), so it is
-        # the path a caller would choose when every GPU has >= 12 host cores to itself, and the plain copy otherwise.
-        cores_per_rank = (os.cpu_count() or 1) // world
+        # Which host-buffer path is the headline `e2e`: the faster of the two, BOTH measured in this run through the same
+        # public call with the copies inside the timed region (`e2e.ascii`, `e2e.host_packed`; one hast_set_option apart).
+        # Packing on the host wins when a GPU has ~14 or more host cores to itself (16-core box, N=1: 385 vs 252 M pairs/s)
+        # and loses when ranks share the cores (24-core box, N=2, 10 threads per rank: 467 vs 504; profiles/r02_y_host_pack.txt).
         e2e["ascii"] = {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step",
                                             "h2d_gbs_per_gpu", "path") if k in e2e}
-        e2e["rule"] = "host_packed when host cores per GPU >= 12 (here %d), else ascii" % cores_per_rank
-        if "host_packed" in e2e and cores_per_rank >= 12:
+        e2e["chosen"] = "ascii"
+        if "host_packed" in e2e and e2e["host_packed"]["value"] > e2e["ascii"]["value"]:
             hpk = e2e["host_packed"]
             e2e.update({"value": hpk["value"], "h2d_bytes_per_step": hpk["h2d_bytes_per_step"], "ms_per_step": hpk["ms_per_step"],
                         "h2d_gbs_per_gpu": hpk["h2d_bytes_per_step"] / (hpk["ms_per_step"] * 1e-3) / 1e9, "path": hpk["path"],
                         "chosen": "host_packed"})
-        else:
-            e2e["chosen"] = "ascii"
+        e2e["rule"] = "the faster of e2e.ascii and e2e.host_packed, both measured in this run"
 
     line = None
     if rank == 0:
