@@ -672,6 +672,9 @@ def leg_cfg2(args, R):
                         "h2d_gbs_per_gpu": hpk["h2d_bytes_per_step"] / (hpk["ms_per_step"] * 1e-3) / 1e9, "path": hpk["path"],
                         "chosen": "host_packed"})
         e2e["rule"] = "the faster of e2e.ascii and e2e.host_packed, both measured in this run"
+        if ceil:                                   # the ceiling is about bytes over PCIe: restate it for the path chosen
+            e2e["ascii"]["frac_of_h2d_ceiling"] = e2e["ascii"]["h2d_gbs_per_gpu"] / ceil
+            e2e["frac_of_h2d_ceiling"] = e2e["h2d_gbs_per_gpu"] / ceil
 
     line = None
     if rank == 0:
