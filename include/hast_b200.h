@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HAST_ABI_VERSION 5
+#define HAST_ABI_VERSION 6
 
 #define HAST_OK            0
 #define HAST_E_ARG        -1   /* bad argument                                            */
