@@ -115,6 +115,10 @@ int run_classify(const Options& opt, RunStats& st) {
     // HAST_PARSE_ONLY=1: host front end only (reader, framing, parseName, interning, ordering);
     // prints barcode \t reads \t bases.  A diagnostic for the host logic, it classifies nothing.
     const bool parse_only = getenv("HAST_PARSE_ONLY") != nullptr;
+    // HAST_PARSE_ONLY=2: the parser also PACKS (the default mode of a real run) and the tally reads the reads back out of
+    // the 2-bit stream: two more columns, a checksum of every read's base codes and the number of reads flagged containN.
+    // Lets the CPU tests check the packed batches the GPU would receive.
+    const bool parse_check = parse_only && atoi(getenv("HAST_PARSE_ONLY")) == 2;
     int n_dev = parse_only ? 1 : hast_device_count();
     if (n_dev <= 0) {
         fprintf(stderr, "ERROR : no CUDA device found; this build of classify has no CPU path\n");
@@ -215,10 +219,11 @@ int run_classify(const Options& opt, RunStats& st) {
         b.cap_bases = block_bytes + 4096;
         b.cap_reads = block_bytes / 24 + 16;
         void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
-        const bool packed = opt.packed_h2d && !parse_only;
+        const bool packed = (opt.packed_h2d && !parse_only) || parse_check;
         b.cap_words = b.cap_bases / 16 + 2;
         if (parse_only) {
-            p0 = malloc(b.cap_bases); p1 = malloc((b.cap_reads + 1) * 4); p2 = malloc(b.cap_reads * 4);
+            p0 = malloc(packed ? b.cap_words * 4 : b.cap_bases); p1 = malloc((b.cap_reads + 1) * 4); p2 = malloc(b.cap_reads * 4);
+            if (packed) p3 = malloc((b.cap_reads / 32 + 2) * 4);
         } else if (hast_host_alloc(&p0, packed ? b.cap_words * 4 : b.cap_bases) ||
                    hast_host_alloc(&p1, (b.cap_reads + 1) * 4) || hast_host_alloc(&p2, b.cap_reads * 4) ||
                    (packed && hast_host_alloc(&p3, (b.cap_reads / 32 + 2) * 4))) {
@@ -232,7 +237,7 @@ int run_classify(const Options& opt, RunStats& st) {
     }
     auto free_batches = [&] {
         for (auto& b : batch_pool) {
-            if (parse_only) { free(b.bases); free(b.read_off); free(b.barcode_id); }
+            if (parse_only) { free(b.bases); free(b.packed); free(b.has_n); free(b.read_off); free(b.barcode_id); }
             else {
                 hast_host_free(b.bases); hast_host_free(b.packed); hast_host_free(b.has_n);
                 hast_host_free(b.read_off); hast_host_free(b.barcode_id);
@@ -356,6 +361,7 @@ int run_classify(const Options& opt, RunStats& st) {
 
     std::atomic<uint64_t> n_reads{0}, n_bases{0};
     std::vector<uint64_t> po_tally;                      // parse-only: reads, bases per barcode id
+    std::vector<uint64_t> po_check;                      // HAST_PARSE_ONLY=2: checksum of the packed base codes, containN reads
     std::vector<std::thread> gpu_threads;
     for (int g = 0; g < n_gpu; ++g)
         gpu_threads.emplace_back([&, g] {
@@ -368,6 +374,14 @@ int run_classify(const Options& opt, RunStats& st) {
                     if (po_tally.size() < 2 * ((size_t)id + 1)) po_tally.resize(2 * ((size_t)id + 1), 0);
                     po_tally[2 * (size_t)id] += 1;
                     po_tally[2 * (size_t)id + 1] += b->read_off[i + 1] - b->read_off[i];
+                    if (parse_check) {
+                        if (po_check.size() < 2 * ((size_t)id + 1)) po_check.resize(2 * ((size_t)id + 1), 0);
+                        uint64_t h = 0;
+                        for (uint32_t g = b->read_off[i]; g < b->read_off[i + 1]; ++g)
+                            h = h * 5u + ((b->packed[g >> 4] >> (30u - 2u * (g & 15u))) & 3u) + 1u;
+                        po_check[2 * (size_t)id] += h;
+                        po_check[2 * (size_t)id + 1] += (b->has_n[i >> 5] >> (i & 31u)) & 1u;
+                    }
                 }
                 n_reads += b->n_reads;
                 n_bases += b->n_bases;
@@ -423,9 +437,15 @@ int run_classify(const Options& opt, RunStats& st) {
         std::vector<uint32_t> order(names.size());
         for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
         std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return names[a] < names[b]; });
-        for (uint32_t id : order)
-            fprintf(table_out, "%s\t%llu\t%llu\n", names[id].c_str(), (unsigned long long)po_tally[2 * (size_t)id],
+        po_check.resize(2 * names.size(), 0);
+        for (uint32_t id : order) {
+            fprintf(table_out, "%s\t%llu\t%llu", names[id].c_str(), (unsigned long long)po_tally[2 * (size_t)id],
                     (unsigned long long)po_tally[2 * (size_t)id + 1]);
+            if (parse_check)
+                fprintf(table_out, "\t%llu\t%llu", (unsigned long long)po_check[2 * (size_t)id],
+                        (unsigned long long)po_check[2 * (size_t)id + 1]);
+            fputc('\n', table_out);
+        }
         fflush(table_out);
         free_batches();
         st.t_total = now() - t_start;

@@ -142,6 +142,44 @@ def test_sliced_reader_equals_serial_reader_on_byte_soup(tmp_path, seed):
         assert parse_only([tmp_path / "s.fq"], threads=4, slice_bytes=slice_bytes) == want, slice_bytes
 
 
+def test_parser_packs_what_the_device_expects(tmp_path):
+    """HAST_PARSE_ONLY=2: the parser runs in its default PACKED mode and the tally reads every read back out of the 2-bit
+    stream.  Checksums of the base codes ((byte >> 1) & 3, kmer.h:11: lower case, IUPAC letters and '\\r' included) and the
+    containN flags (upper-case 'N' only, classify.cpp:182-185) per barcode must equal a direct computation, for plain and
+    gzip input, tiny slices and blocks (reads straddle words, batches, slices)."""
+    rng = np.random.default_rng(5)
+    letters = np.frombuffer(b"ACGTACGTACGTNnacgtRY", np.uint8)
+    heads, reads = [], []
+    for i in range(4000):
+        heads.append(b"@r%d#%d_%d_%d/1" % (i, *rng.integers(1, 30, 3)))
+        reads.append(letters[rng.integers(0, letters.size, int(rng.integers(0, 260)))].tobytes())
+    cases.write_fastq(tmp_path / "p.fq", heads, reads)
+    cases.write_fastq(tmp_path / "p.fq.gz", heads, reads)
+    mask = (1 << 64) - 1
+    n, bsum, hsum, nn = Counter(), Counter(), Counter(), Counter()
+    for h, r in zip(heads, reads):
+        bc = orc.parse_name(h)
+        n[bc] += 1
+        bsum[bc] += len(r)
+        x = 0
+        for c in r:
+            x = (x * 5 + ((c >> 1) & 3) + 1) & mask
+        hsum[bc] = (hsum[bc] + x) & mask
+        nn[bc] += b"N" in r
+    want = b"".join(b"%s\t%d\t%d\t%d\t%d\n" % (k, n[k], bsum[k], hsum[k], nn[k]) for k in sorted(n))
+
+    def run_check(files, **env):
+        r = run([CLASSIFY, "--hap0", "x", "--hap1", "y", "-t", "3"] + [a for f in files for a in ("--read", f)],
+                env=dict(os.environ, HAST_PARSE_ONLY="2", **env))
+        assert r.returncode == 0, r.stderr[-400:]
+        return r.stdout
+
+    assert run_check([tmp_path / "p.fq"]) == want
+    assert run_check([tmp_path / "p.fq"], HAST_SLICE_BYTES="777") == want
+    assert run_check([tmp_path / "p.fq.gz"], HAST_BLOCK_MB="0", HAST_INFLATE_THREADS="3") == want
+    assert run_check([tmp_path / "p.fq"], HAST_SERIAL_READER="1", HAST_BLOCK_MB="0") == want
+
+
 def test_tiny_records_fill_a_batch_before_the_block_ends(tmp_path):
     """Records far shorter than the batch buffers were sized for: the block is parsed into several batches."""
     n = 700_000
